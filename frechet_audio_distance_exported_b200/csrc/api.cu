@@ -1,0 +1,692 @@
+// api.cu — the C ABI of libfadb200.so (see include/fadb.h): handle lifetime, weight ingestion,
+// the per-model layer schedules and the host-buffer end-to-end path.
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fadb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int embed_dim(int model) {
+    switch (model) {
+        case FADB_MODEL_VGGISH: return 128;
+        case FADB_MODEL_PANN8K:
+        case FADB_MODEL_PANN16K:
+        case FADB_MODEL_PANN32K: return 2048;
+        case FADB_MODEL_CLAP: return 512;
+        default: return -1;
+    }
+}
+
+// ---------------------------------------------------------------- conv1 packing ([64][1][3][3] -> [9][64])
+__global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * 64) {
+        const int tap = i / 64, co = i % 64;
+        float v = w[co * 9 + tap];
+        if (scale) v *= scale[co];
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------- CNN14 tail
+// x [B, Ht, Wf, C] bf16 (hi + optional lo) -> mean over Wf, then max over Ht + mean over Ht  (pann.py:263-268)
+__global__ void cnn14_global_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                         int Ht, int Wf, int C, __nv_bfloat16* __restrict__ ohi,
+                                         __nv_bfloat16* __restrict__ olo) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const size_t base = (size_t)b * Ht * Wf * C + c;
+    float mx = -INFINITY, sum = 0.f;
+    for (int t = 0; t < Ht; ++t) {
+        float m = 0.f;
+        for (int f = 0; f < Wf; ++f) {
+            const size_t o = base + ((size_t)t * Wf + f) * C;
+            float v = __bfloat162float(hi[o]);
+            if (lo) v += __bfloat162float(lo[o]);
+            m += v;
+        }
+        m /= (float)Wf;
+        mx = fmaxf(mx, m);
+        sum += m;
+    }
+    const float r = mx + sum / (float)Ht;
+    const __nv_bfloat16 h = __float2bfloat16_rn(r);
+    ohi[(size_t)b * C + c] = h;
+    if (olo) olo[(size_t)b * C + c] = __float2bfloat16_rn(r - __bfloat162float(h));
+}
+
+__global__ void l2_normalize_kernel(float* __restrict__ x, int d) {   // F.normalize(dim=-1), eps 1e-12
+    __shared__ float red[32];
+    float* row = x + (size_t)blockIdx.x * d;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) s += row[i] * row[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    const float inv = 1.f / fmaxf(sqrtf(red[0]), 1e-12f);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) row[i] *= inv;
+}
+
+int launch_cnn14_global_pool(fadb_handle* h, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t B, int Ht,
+                             int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+    dim3 grid((C + 255) / 256, (unsigned)B);
+    const bool x3 = h->precision == FADB_PREC_BF16X3;
+    cnn14_global_pool_kernel<<<grid, 256, 0, st>>>(x_hi, x3 ? x_lo : nullptr, Ht, Wf, C, out_hi, x3 ? out_lo : nullptr);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+int launch_l2_normalize(fadb_handle* h, float* x, int64_t rows, int d, cudaStream_t st) {
+    if (rows <= 0) return FADB_OK;
+    l2_normalize_kernel<<<(unsigned)rows, 256, 0, st>>>(x, d);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+// ---------------------------------------------------------------- weights
+static void free_layers(fadb_handle* h) {
+    for (auto& L : h->layers) {
+        if (L.w_hi) cudaFree(L.w_hi);
+        if (L.w_lo) cudaFree(L.w_lo);
+        if (L.bias) cudaFree(L.bias);
+    }
+    h->layers.clear();
+    if (h->conv1_w) cudaFree(h->conv1_w);
+    if (h->conv1_b) cudaFree(h->conv1_b);
+    if (h->bn0_scale) cudaFree(h->bn0_scale);
+    if (h->bn0_shift) cudaFree(h->bn0_shift);
+    h->conv1_w = h->conv1_b = h->bn0_scale = h->bn0_shift = nullptr;
+    h->weights_ready = false;
+}
+static void free_staged(fadb_handle* h) {
+    for (auto& kv : h->staged)
+        if (kv.second.dev) cudaFree(kv.second.dev);
+    h->staged.clear();
+}
+
+static int get_staged(fadb_handle* h, const std::string& name, std::initializer_list<int64_t> shape, const float** out) {
+    auto it = h->staged.find(name);
+    if (it == h->staged.end()) {
+        set_error("missing weight tensor '%s'", name.c_str());
+        return FADB_E_STATE;
+    }
+    const HostTensor& t = it->second;
+    bool ok = t.shape.size() == shape.size();
+    size_t i = 0;
+    for (int64_t s : shape) {
+        if (ok && t.shape[i] != s) ok = false;
+        ++i;
+    }
+    if (!ok) {
+        set_error("weight tensor '%s' has the wrong shape", name.c_str());
+        return FADB_E_INVALID;
+    }
+    *out = t.dev;
+    return FADB_OK;
+}
+
+// pack one tensor-core layer from a staged weight (+ optional bias / folded BN)
+static int add_layer(fadb_handle* h, const float* w, int Cout, int Cin, int ksize, const float* scale,
+                     const float* bias_or_shift, cudaStream_t st) {
+    PackedLayer L;
+    L.N = Cout;
+    L.Cin = Cin;
+    L.taps = ksize * ksize;
+    L.K = L.taps * Cin;
+    const size_t n = (size_t)L.N * L.K;
+    FADB_CUDA_CHECK(cudaMalloc(&L.w_hi, n * sizeof(__nv_bfloat16)));
+    FADB_CUDA_CHECK(cudaMalloc(&L.w_lo, n * sizeof(__nv_bfloat16)));
+    FADB_CUDA_CHECK(cudaMalloc(&L.bias, (size_t)Cout * sizeof(float)));
+    FADB_CHECK(pack_conv_weight(h, w, Cout, Cin, ksize, scale, L.w_hi, L.w_lo, st));
+    if (bias_or_shift)
+        FADB_CUDA_CHECK(cudaMemcpyAsync(L.bias, bias_or_shift, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else
+        FADB_CUDA_CHECK(cudaMemsetAsync(L.bias, 0, (size_t)Cout * sizeof(float), st));
+    h->layers.push_back(L);
+    return FADB_OK;
+}
+
+static int commit_vggish(fadb_handle* h, cudaStream_t st) {
+    static const int slots[6] = {0, 3, 6, 8, 11, 13};
+    static const int chans[7] = {1, 64, 128, 256, 256, 512, 512};
+    char name[64];
+    const float *w, *b;
+    snprintf(name, sizeof(name), "features.0.weight");
+    FADB_CHECK(get_staged(h, name, {64, 1, 3, 3}, &w));
+    FADB_CHECK(get_staged(h, "features.0.bias", {64}, &b));
+    FADB_CUDA_CHECK(cudaMalloc(&h->conv1_w, 9 * 64 * sizeof(float)));
+    FADB_CUDA_CHECK(cudaMalloc(&h->conv1_b, 64 * sizeof(float)));
+    pack_conv1_kernel<<<3, 256, 0, st>>>(w, nullptr, h->conv1_w);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaMemcpyAsync(h->conv1_b, b, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int i = 1; i < 6; ++i) {
+        snprintf(name, sizeof(name), "features.%d.weight", slots[i]);
+        FADB_CHECK(get_staged(h, name, {chans[i + 1], chans[i], 3, 3}, &w));
+        snprintf(name, sizeof(name), "features.%d.bias", slots[i]);
+        FADB_CHECK(get_staged(h, name, {chans[i + 1]}, &b));
+        FADB_CHECK(add_layer(h, w, chans[i + 1], chans[i], 3, nullptr, b, st));
+    }
+    static const int fslot[3] = {0, 2, 4};
+    static const int fin[3] = {12288, 4096, 4096}, fout[3] = {4096, 4096, 128};
+    for (int i = 0; i < 3; ++i) {
+        snprintf(name, sizeof(name), "embeddings.%d.weight", fslot[i]);
+        FADB_CHECK(get_staged(h, name, {fout[i], fin[i]}, &w));
+        snprintf(name, sizeof(name), "embeddings.%d.bias", fslot[i]);
+        FADB_CHECK(get_staged(h, name, {fout[i]}, &b));
+        FADB_CHECK(add_layer(h, w, fout[i], fin[i], 1, nullptr, b, st));
+    }
+    return FADB_OK;
+}
+
+static int folded_bn(fadb_handle* h, const std::string& prefix, int C, float** scale, float** shift, cudaStream_t st) {
+    const float *g, *b, *m, *v;
+    FADB_CHECK(get_staged(h, prefix + ".weight", {C}, &g));
+    FADB_CHECK(get_staged(h, prefix + ".bias", {C}, &b));
+    FADB_CHECK(get_staged(h, prefix + ".running_mean", {C}, &m));
+    FADB_CHECK(get_staged(h, prefix + ".running_var", {C}, &v));
+    FADB_CUDA_CHECK(cudaMalloc(scale, C * sizeof(float)));
+    FADB_CUDA_CHECK(cudaMalloc(shift, C * sizeof(float)));
+    return fold_bn(h, g, b, m, v, C, *scale, *shift, st);
+}
+
+static int commit_cnn14(fadb_handle* h, bool clap, cudaStream_t st) {
+    static const int ch[7] = {1, 64, 128, 256, 512, 1024, 2048};
+    FADB_CHECK(folded_bn(h, "bn0", 64, &h->bn0_scale, &h->bn0_shift, st));
+    std::vector<float*> tmp;
+    int rc = FADB_OK;
+    for (int blk = 1; blk <= 6 && rc == FADB_OK; ++blk) {
+        for (int cv = 1; cv <= 2 && rc == FADB_OK; ++cv) {
+            const int cin = (cv == 1) ? ch[blk - 1] : ch[blk], cout = ch[blk];
+            char wname[64], bname[64];
+            snprintf(wname, sizeof(wname), "conv_block%d.conv%d.weight", blk, cv);
+            snprintf(bname, sizeof(bname), "conv_block%d.bn%d", blk, cv);
+            const float* w;
+            rc = get_staged(h, wname, {cout, cin, 3, 3}, &w);
+            if (rc != FADB_OK) break;
+            float *scale = nullptr, *shift = nullptr;
+            rc = folded_bn(h, bname, cout, &scale, &shift, st);
+            tmp.push_back(scale);
+            tmp.push_back(shift);
+            if (rc != FADB_OK) break;
+            if (blk == 1 && cv == 1) {
+                if (cudaMalloc(&h->conv1_w, 9 * 64 * sizeof(float)) != cudaSuccess ||
+                    cudaMalloc(&h->conv1_b, 64 * sizeof(float)) != cudaSuccess) {
+                    set_error("cudaMalloc conv1 failed");
+                    rc = FADB_E_NOMEM;
+                    break;
+                }
+                pack_conv1_kernel<<<3, 256, 0, st>>>(w, scale, h->conv1_w);
+                h->launches++;
+                cudaMemcpyAsync(h->conv1_b, shift, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            } else {
+                rc = add_layer(h, w, cout, cin, 3, scale, shift, st);
+            }
+        }
+    }
+    if (rc == FADB_OK) {
+        const float *w, *b;
+        rc = get_staged(h, "fc1.weight", {2048, 2048}, &w);
+        if (rc == FADB_OK) rc = get_staged(h, "fc1.bias", {2048}, &b);
+        if (rc == FADB_OK) rc = add_layer(h, w, 2048, 2048, 1, nullptr, b, st);
+        if (rc == FADB_OK && clap) {
+            rc = get_staged(h, "clap_head.0.weight", {512, 2048}, &w);
+            if (rc == FADB_OK) rc = get_staged(h, "clap_head.0.bias", {512}, &b);
+            if (rc == FADB_OK) rc = add_layer(h, w, 512, 2048, 1, nullptr, b, st);
+            if (rc == FADB_OK) rc = get_staged(h, "clap_head.2.weight", {512, 512}, &w);
+            if (rc == FADB_OK) rc = get_staged(h, "clap_head.2.bias", {512}, &b);
+            if (rc == FADB_OK) rc = add_layer(h, w, 512, 512, 1, nullptr, b, st);
+        }
+    }
+    cudaStreamSynchronize(st);
+    for (float* p : tmp)
+        if (p) cudaFree(p);
+    return rc;
+}
+
+// ---------------------------------------------------------------- layer schedules
+static inline __nv_bfloat16* lo_plane(fadb_handle* h, int buf, size_t plane_elems) {
+    return h->ws_act[buf].as<__nv_bfloat16>() + plane_elems;
+}
+
+constexpr size_t kVggishActElems = 98304;        // max activation elements per patch (48*32*64)
+
+static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* emb, cudaStream_t st) {
+    const size_t plane = (size_t)h->max_batch * kVggishActElems;
+    FADB_CHECK(h->ws_act[0].reserve(plane * 2 * sizeof(__nv_bfloat16)));
+    FADB_CHECK(h->ws_act[1].reserve(plane * 2 * sizeof(__nv_bfloat16)));
+    __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
+    __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
+    const int B = (int)P;
+    FADB_CHECK(launch_conv1_vggish(h, feats, P, a[0], l[0], st));                       // [P,48,32,64]
+    struct Step { int H, W, Cin, pool; };
+    static const Step steps[5] = {{48, 32, 64, 1}, {24, 16, 128, 0}, {24, 16, 256, 1}, {12, 8, 256, 0}, {12, 8, 512, 1}};
+    int cur = 0;
+    for (int i = 0; i < 5; ++i) {
+        LayerIO io;
+        io.in_hi = a[cur]; io.in_lo = l[cur];
+        io.B = B; io.H = steps[i].H; io.W = steps[i].W; io.Cin = steps[i].Cin;
+        io.taps = 9; io.relu = 1; io.pool = steps[i].pool;
+        io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+        FADB_CHECK(launch_gemm_layer(h, h->layers[i], io, st));
+        cur ^= 1;
+    }
+    // NHWC flatten (vggish.py:91-94) is the memory order already: [P, 6*4*512]
+    static const int fin[3] = {12288, 4096, 4096};
+    for (int i = 0; i < 3; ++i) {
+        LayerIO io;
+        io.in_hi = a[cur]; io.in_lo = l[cur];
+        io.B = 1; io.H = 1; io.W = B; io.Cin = fin[i];
+        io.taps = 1; io.relu = (i < 2); io.pool = 0;
+        if (i < 2) { io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1]; }
+        else io.out_f32 = emb;                                                          // no final ReLU, vggish.py:76-77
+        FADB_CHECK(launch_gemm_layer(h, h->layers[5 + i], io, st));
+        cur ^= 1;
+    }
+    return FADB_OK;
+}
+
+static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T, float* emb, cudaStream_t st) {
+    const int B = (int)B64;
+    const size_t per_clip = (size_t)T * 64 * 64;
+    const size_t plane = (size_t)h->max_batch_cnn14 * per_clip;
+    FADB_CHECK(h->ws_act[0].reserve(plane * 2 * sizeof(__nv_bfloat16)));
+    FADB_CHECK(h->ws_act[1].reserve(plane * 2 * sizeof(__nv_bfloat16)));
+    __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
+    __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
+    FADB_CHECK(launch_conv1_cnn14(h, feats, B, T, a[0], l[0], st));                     // [B,T,64,64]
+    int cur = 0, H = T, W = 64, C = 64, li = 0;
+    for (int blk = 1; blk <= 6; ++blk) {
+        for (int cv = 1; cv <= 2; ++cv) {
+            if (blk == 1 && cv == 1) continue;
+            LayerIO io;
+            io.in_hi = a[cur]; io.in_lo = l[cur];
+            io.B = B; io.H = H; io.W = W; io.Cin = C;
+            io.taps = 9; io.relu = 1;
+            io.pool = (cv == 2 && blk < 6) ? 2 : 0;                                     // avg_pool2d, pann.py:192,255-260
+            io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+            FADB_CHECK(launch_gemm_layer(h, h->layers[li], io, st));
+            C = h->layers[li].N;
+            ++li;
+            cur ^= 1;
+            if (io.pool) { H /= 2; W /= 2; }
+        }
+    }
+    // global pooling -> [B, 2048]
+    FADB_CHECK(launch_cnn14_global_pool(h, a[cur], l[cur], B, H, W, C, a[cur ^ 1], l[cur ^ 1], st));
+    cur ^= 1;
+    const bool clap = (h->model == FADB_MODEL_CLAP);
+    {
+        LayerIO io;
+        io.in_hi = a[cur]; io.in_lo = l[cur];
+        io.B = 1; io.H = 1; io.W = B; io.Cin = 2048; io.taps = 1; io.relu = 1; io.pool = 0;     // pann.py:271
+        if (clap) { io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1]; }
+        else io.out_f32 = emb;
+        FADB_CHECK(launch_gemm_layer(h, h->layers[li++], io, st));
+        cur ^= 1;
+    }
+    if (clap) {
+        LayerIO io;
+        io.in_hi = a[cur]; io.in_lo = l[cur];
+        io.B = 1; io.H = 1; io.W = B; io.Cin = 2048; io.taps = 1; io.relu = 1; io.pool = 0;
+        io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+        FADB_CHECK(launch_gemm_layer(h, h->layers[li++], io, st));
+        cur ^= 1;
+        LayerIO io2;
+        io2.in_hi = a[cur]; io2.in_lo = l[cur];
+        io2.B = 1; io2.H = 1; io2.W = B; io2.Cin = 512; io2.taps = 1; io2.relu = 0; io2.pool = 0;
+        io2.out_f32 = emb;
+        FADB_CHECK(launch_gemm_layer(h, h->layers[li++], io2, st));
+        FADB_CHECK(launch_l2_normalize(h, emb, B, 512, st));
+    }
+    return FADB_OK;
+}
+
+static int check_device_flag(fadb_handle* h) {
+    if (h->err_flag_host && *h->err_flag_host != 0) {
+        set_error("device-side failure flag = %d (1 = pipeline timeout, 2 = non-finite result)", *h->err_flag_host);
+        return FADB_E_DEVICE;
+    }
+    return FADB_OK;
+}
+
+}  // namespace fadb
+
+using namespace fadb;
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+int fadb_abi_version(void) { return FADB_ABI_VERSION; }
+const char* fadb_last_error(void) { return g_err; }
+
+int fadb_create(fadb_handle** out, int device) {
+    if (!out) { set_error("fadb_create: out is NULL"); return FADB_E_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s): libfadb200 has no CPU fallback", cudaGetErrorString(e));
+        return FADB_E_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (%d devices)", device, count); return FADB_E_INVALID; }
+    FADB_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FADB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libfadb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return FADB_E_CUDA;
+    }
+    fadb_handle* h = new fadb_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    FADB_CUDA_CHECK(cudaHostAlloc(&h->err_flag_host, sizeof(int), cudaHostAllocMapped));
+    *h->err_flag_host = 0;
+    FADB_CUDA_CHECK(cudaHostGetDevicePointer(&h->err_flag, h->err_flag_host, 0));
+    FADB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+        FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_compute[i], cudaEventDisableTiming));
+    }
+    int rc = gemm_init(h);
+    if (rc == FADB_OK) rc = frontend_init(h);
+    if (rc != FADB_OK) { fadb_destroy(h); return rc; }
+    *out = h;
+    return FADB_OK;
+}
+
+void fadb_destroy(fadb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_layers(h);
+    free_staged(h);
+    h->weight_pool.release();
+    h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
+    h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+        if (h->ev_compute[i]) cudaEventDestroy(h->ev_compute[i]);
+    }
+    if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+    delete h;
+}
+
+int fadb_set_precision(fadb_handle* h, int prec) {
+    if (!h || (prec != FADB_PREC_BF16 && prec != FADB_PREC_BF16X3)) { set_error("bad precision"); return FADB_E_INVALID; }
+    h->precision = prec;
+    return FADB_OK;
+}
+
+int fadb_set_max_batch(fadb_handle* h, int max_items) {
+    if (!h || max_items < 1 || max_items > 65535) { set_error("max_batch must be in [1, 65535]"); return FADB_E_INVALID; }
+    h->max_batch = max_items;
+    h->max_batch_cnn14 = max_items;
+    return FADB_OK;
+}
+
+int fadb_weights_begin(fadb_handle* h, int model) {
+    if (!h || embed_dim(model) < 0) { set_error("unknown model %d", model); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    free_staged(h);
+    h->staged_model = model;
+    return FADB_OK;
+}
+
+int fadb_weights_tensor(fadb_handle* h, const char* name, const float* data_host, const int64_t* shape, int ndim) {
+    if (!h || !name || !data_host || ndim < 0 || ndim > 4) { set_error("bad weights_tensor arguments"); return FADB_E_INVALID; }
+    if (h->staged_model < 0) { set_error("fadb_weights_tensor before fadb_weights_begin"); return FADB_E_STATE; }
+    cudaSetDevice(h->device);
+    HostTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
+    FADB_CUDA_CHECK(cudaMalloc(&t.dev, (t.numel ? t.numel : 1) * sizeof(float)));
+    FADB_CUDA_CHECK(cudaMemcpy(t.dev, data_host, t.numel * sizeof(float), cudaMemcpyHostToDevice));
+    auto it = h->staged.find(name);
+    if (it != h->staged.end() && it->second.dev) cudaFree(it->second.dev);
+    h->staged[name] = t;
+    return FADB_OK;
+}
+
+int fadb_weights_commit(fadb_handle* h) {
+    if (!h || h->staged_model < 0) { set_error("fadb_weights_commit before fadb_weights_begin"); return FADB_E_STATE; }
+    cudaSetDevice(h->device);
+    free_layers(h);
+    cudaStream_t st = 0;
+    int rc = (h->staged_model == FADB_MODEL_VGGISH) ? commit_vggish(h, st)
+                                                    : commit_cnn14(h, h->staged_model == FADB_MODEL_CLAP, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    free_staged(h);
+    if (rc != FADB_OK) { free_layers(h); return rc; }
+    if (e != cudaSuccess) { set_error("weight packing failed: %s", cudaGetErrorString(e)); free_layers(h); return FADB_E_CUDA; }
+    h->model = h->staged_model;
+    h->staged_model = -1;
+    h->weights_ready = true;
+    return FADB_OK;
+}
+
+int64_t fadb_frontend_rows(int model, int64_t n_samples) { return frontend_rows(model, n_samples); }
+
+int fadb_frontend(fadb_handle* h, int model, const float* pcm_dev, int64_t n_clips, int64_t n_samples,
+                  int64_t pcm_stride, float* feats_dev, void* stream) {
+    if (!h || !pcm_dev || !feats_dev) { set_error("fadb_frontend: NULL argument"); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    const int64_t kMax = 32768;
+    const int64_t rows = frontend_rows(model, n_samples);
+    if (rows < 0) { set_error("unknown model %d", model); return FADB_E_INVALID; }
+    const int64_t row_elems = (model == FADB_MODEL_VGGISH) ? 96 * 64 : 64;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += kMax) {
+        const int64_t nc = (n_clips - c0 < kMax) ? n_clips - c0 : kMax;
+        FADB_CHECK(launch_frontend(h, model, pcm_dev + c0 * pcm_stride, nc, n_samples, pcm_stride,
+                                   feats_dev + c0 * rows * row_elems, (cudaStream_t)stream));
+    }
+    return FADB_OK;
+}
+
+int fadb_embed_dim(int model) { return embed_dim(model); }
+
+int fadb_embed(fadb_handle* h, const float* feats_dev, int64_t n_items, int64_t t_frames, float* emb_dev, void* stream) {
+    if (!h || !feats_dev || !emb_dev) { set_error("fadb_embed: NULL argument"); return FADB_E_INVALID; }
+    if (!h->weights_ready) { set_error("fadb_embed: weights not committed"); return FADB_E_STATE; }
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = embed_dim(h->model);
+    if (h->model == FADB_MODEL_VGGISH) {
+        if (t_frames != 96) { set_error("VGGish patches have 96 frames, got %lld", (long long)t_frames); return FADB_E_INVALID; }
+        for (int64_t i0 = 0; i0 < n_items; i0 += h->max_batch) {
+            const int64_t n = (n_items - i0 < h->max_batch) ? n_items - i0 : h->max_batch;
+            FADB_CHECK(vggish_forward(h, feats_dev + i0 * 96 * 64, n, emb_dev + i0 * d, st));
+        }
+    } else {
+        if (t_frames < 32 || t_frames > 16384) { set_error("CNN14 needs 32 <= T <= 16384 frames, got %lld", (long long)t_frames); return FADB_E_INVALID; }
+        for (int64_t i0 = 0; i0 < n_items; i0 += h->max_batch_cnn14) {
+            const int64_t n = (n_items - i0 < h->max_batch_cnn14) ? n_items - i0 : h->max_batch_cnn14;
+            FADB_CHECK(cnn14_forward(h, feats_dev + i0 * t_frames * 64, n, (int)t_frames, emb_dev + i0 * d, st));
+        }
+    }
+    return check_device_flag(h);
+}
+
+int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                   float* emb_dev, void* stream) {
+    if (!h || !pcm_dev || !emb_dev) { set_error("fadb_embed_pcm: NULL argument"); return FADB_E_INVALID; }
+    if (!h->weights_ready) { set_error("fadb_embed_pcm: weights not committed"); return FADB_E_STATE; }
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int model = h->model;
+    const int64_t rows = frontend_rows(model, n_samples);
+    if (rows <= 0) return FADB_OK;       // clips too short: zero rows, like waveform_to_examples -> [0,1,96,64]
+    const int d = embed_dim(model);
+    if (model == FADB_MODEL_VGGISH) {
+        int64_t cpc = h->max_batch / rows;                  // clips per chunk
+        if (cpc < 1) { set_error("max_batch %d smaller than patches per clip %lld", h->max_batch, (long long)rows); return FADB_E_INVALID; }
+        FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 96 * 64 * sizeof(float)));
+        for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
+            const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+            FADB_CHECK(launch_frontend(h, model, pcm_dev + c0 * pcm_stride, nc, n_samples, pcm_stride,
+                                       h->ws_feats.as<float>(), st));
+            FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb_dev + c0 * rows * d, st));
+        }
+    } else {
+        const int64_t cpc = h->max_batch_cnn14;
+        FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 64 * sizeof(float)));
+        for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
+            const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+            FADB_CHECK(launch_frontend(h, model, pcm_dev + c0 * pcm_stride, nc, n_samples, pcm_stride,
+                                       h->ws_feats.as<float>(), st));
+            FADB_CHECK(cnn14_forward(h, h->ws_feats.as<float>(), nc, (int)rows, emb_dev + c0 * d, st));
+        }
+    }
+    return check_device_flag(h);
+}
+
+int fadb_stats_accumulate(fadb_handle* h, const float* emb_dev, int64_t n_rows, int d, int64_t row_stride,
+                          const double* shift_dev, double* acc_dev, void* stream) {
+    if (!h || !emb_dev || !acc_dev) { set_error("fadb_stats_accumulate: NULL argument"); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    return launch_stats_accumulate(h, emb_dev, n_rows, d, row_stride, shift_dev, acc_dev, (cudaStream_t)stream);
+}
+
+int fadb_stats_accumulate_f64(fadb_handle* h, const double* emb_dev, int64_t n_rows, int d, int64_t row_stride,
+                              const double* shift_dev, double* acc_dev, void* stream) {
+    if (!h || !emb_dev || !acc_dev) { set_error("fadb_stats_accumulate_f64: NULL argument"); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    return launch_stats_accumulate_f64(h, emb_dev, n_rows, d, row_stride, shift_dev, acc_dev, (cudaStream_t)stream);
+}
+
+int fadb_stats_finalize(fadb_handle* h, const double* acc_dev, int d, const double* shift_dev, double* mu_dev,
+                        double* sigma_dev, void* stream) {
+    if (!h || !acc_dev || !sigma_dev) { set_error("fadb_stats_finalize: NULL argument"); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    return launch_stats_finalize(h, acc_dev, d, shift_dev, mu_dev, sigma_dev, (cudaStream_t)stream);
+}
+
+int fadb_frechet(fadb_handle* h, const double* mu1_dev, const double* sigma1_dev, const double* mu2_dev,
+                 const double* sigma2_dev, int d, double* out_dev, void* stream) {
+    if (!h || !mu1_dev || !sigma1_dev || !mu2_dev || !sigma2_dev || !out_dev) { set_error("fadb_frechet: NULL argument"); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    return launch_frechet(h, mu1_dev, sigma1_dev, mu2_dev, sigma2_dev, d, out_dev, (cudaStream_t)stream);
+}
+
+int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_bg, const float* pcm_ev_host,
+                           int64_t n_ev, int64_t n_samples, float* emb_bg_host, float* emb_ev_host, double* fad_out) {
+    if (!h || !pcm_bg_host || !pcm_ev_host || !fad_out) { set_error("fadb_fad_from_pcm_host: NULL argument"); return FADB_E_INVALID; }
+    if (!h->weights_ready) { set_error("weights not committed"); return FADB_E_STATE; }
+    cudaSetDevice(h->device);
+    const int model = h->model;
+    const int d = embed_dim(model);
+    const int64_t rows = (model == FADB_MODEL_VGGISH) ? frontend_rows(model, n_samples) : 1;
+    if (rows <= 0 || n_bg <= 0 || n_ev <= 0) { set_error("empty embedding set (fad.py:640-645)"); return FADB_E_INVALID; }
+    int64_t cpc = (model == FADB_MODEL_VGGISH) ? h->max_batch / rows : h->max_batch_cnn14;
+    if (cpc < 1) cpc = 1;
+    const size_t acc_n = 1 + (size_t)d + (size_t)d * d;
+    // stats workspace: acc[2] | mu[2] | sigma[2] | out[4]
+    FADB_CHECK(h->ws_stats.reserve((2 * acc_n + 2 * (size_t)d + 2 * (size_t)d * d + 8) * sizeof(double)));
+    double* acc[2] = {h->ws_stats.as<double>(), h->ws_stats.as<double>() + acc_n};
+    double* mu[2] = {acc[1] + acc_n, acc[1] + acc_n + d};
+    double* sg[2] = {mu[1] + d, mu[1] + d + (size_t)d * d};
+    double* outd = sg[1] + (size_t)d * d;
+    FADB_CHECK(h->ws_pcm[0].reserve((size_t)cpc * n_samples * sizeof(float)));
+    FADB_CHECK(h->ws_pcm[1].reserve((size_t)cpc * n_samples * sizeof(float)));
+    FADB_CHECK(h->ws_emb.reserve((size_t)cpc * rows * d * sizeof(float) * 2));
+    cudaStream_t cs = h->copy_stream;
+    cudaStream_t st = 0;   // legacy default stream orders against nothing else here; use a dedicated one
+    static thread_local cudaStream_t s_compute = nullptr;
+    if (!s_compute) FADB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking));
+    st = s_compute;
+    FADB_CUDA_CHECK(cudaMemsetAsync(acc[0], 0, 2 * acc_n * sizeof(double), st));
+    int buf = 0;
+    int64_t chunk_idx = 0;
+    for (int set = 0; set < 2; ++set) {
+        const float* src = set == 0 ? pcm_bg_host : pcm_ev_host;
+        float* emb_host = set == 0 ? emb_bg_host : emb_ev_host;
+        const int64_t n = set == 0 ? n_bg : n_ev;
+        for (int64_t c0 = 0; c0 < n; c0 += cpc, ++chunk_idx) {
+            const int64_t nc = (n - c0 < cpc) ? n - c0 : cpc;
+            float* dpcm = h->ws_pcm[buf].as<float>();
+            float* demb = h->ws_emb.as<float>() + (size_t)buf * cpc * rows * d;
+            if (chunk_idx >= 2) FADB_CUDA_CHECK(cudaStreamWaitEvent(cs, h->ev_compute[buf], 0));   // buffer free again
+            FADB_CUDA_CHECK(cudaMemcpyAsync(dpcm, src + c0 * n_samples, (size_t)nc * n_samples * sizeof(float),
+                                            cudaMemcpyHostToDevice, cs));
+            FADB_CUDA_CHECK(cudaEventRecord(h->ev_copy[buf], cs));
+            FADB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_copy[buf], 0));
+            FADB_CHECK(fadb_embed_pcm(h, dpcm, nc, n_samples, n_samples, demb, st));
+            FADB_CHECK(launch_stats_accumulate(h, demb, nc * rows, d, d, nullptr, acc[set], st));
+            if (emb_host)
+                FADB_CUDA_CHECK(cudaMemcpyAsync(emb_host + c0 * rows * d, demb, (size_t)nc * rows * d * sizeof(float),
+                                                cudaMemcpyDeviceToHost, st));
+            FADB_CUDA_CHECK(cudaEventRecord(h->ev_compute[buf], st));
+            buf ^= 1;
+        }
+    }
+    for (int set = 0; set < 2; ++set) FADB_CHECK(launch_stats_finalize(h, acc[set], d, nullptr, mu[set], sg[set], st));
+    FADB_CHECK(launch_frechet(h, mu[0], sg[0], mu[1], sg[1], d, outd, st));
+    double res[4];
+    FADB_CUDA_CHECK(cudaMemcpyAsync(res, outd, sizeof(res), cudaMemcpyDeviceToHost, st));
+    FADB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *fad_out = res[0];
+    return check_device_flag(h);
+}
+
+int64_t fadb_launch_count(const fadb_handle* h) { return h ? h->launches : 0; }
+
+int fadb_device_status(fadb_handle* h) { return (h && h->err_flag_host) ? *h->err_flag_host : 0; }
+
+// single tensor-core layer for parity tests of the implicit-GEMM kernel
+int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, int Cin, const float* w_dev,
+                          const float* bias_dev, int Cout, int ksize, int relu, int pool, float* out, void* stream) {
+    if (!h || !x || !w_dev || !out) { set_error("fadb_debug_conv_layer: NULL argument"); return FADB_E_INVALID; }
+    if (ksize != 3 && ksize != 1) { set_error("ksize must be 1 or 3"); return FADB_E_INVALID; }
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_in = (size_t)B * H * W * Cin;
+    __nv_bfloat16 *xh = nullptr, *xl = nullptr;
+    FADB_CUDA_CHECK(cudaMalloc(&xh, n_in * 2));
+    FADB_CUDA_CHECK(cudaMalloc(&xl, n_in * 2));
+    int rc = split_f32_to_bf16(h, x, (int64_t)n_in, xh, xl, st);
+    PackedLayer L;
+    L.N = Cout; L.Cin = Cin; L.taps = ksize * ksize; L.K = L.taps * Cin;
+    const size_t nw = (size_t)L.N * L.K;
+    if (rc == FADB_OK && (cudaMalloc(&L.w_hi, nw * 2) != cudaSuccess || cudaMalloc(&L.w_lo, nw * 2) != cudaSuccess)) {
+        set_error("cudaMalloc failed");
+        rc = FADB_E_NOMEM;
+    }
+    if (rc == FADB_OK) rc = pack_conv_weight(h, w_dev, Cout, Cin, ksize, nullptr, L.w_hi, L.w_lo, st);
+    L.bias = const_cast<float*>(bias_dev);
+    if (rc == FADB_OK) {
+        LayerIO io;
+        io.in_hi = xh; io.in_lo = xl; io.B = B; io.H = H; io.W = W; io.Cin = Cin;
+        io.taps = L.taps; io.relu = relu; io.pool = pool; io.out_f32 = out;
+        rc = launch_gemm_layer(h, L, io, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (xh) cudaFree(xh);
+    if (xl) cudaFree(xl);
+    if (L.w_hi) cudaFree(L.w_hi);
+    if (L.w_lo) cudaFree(L.w_lo);
+    if (rc != FADB_OK) return rc;
+    if (e != cudaSuccess) { set_error("debug conv layer failed: %s", cudaGetErrorString(e)); return FADB_E_CUDA; }
+    return check_device_flag(h);
+}
+
+}  // extern "C"

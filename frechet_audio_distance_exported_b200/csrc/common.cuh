@@ -1,0 +1,182 @@
+// common.cuh — shared declarations of libfadb200 (B200 / sm_100a FAD hot path).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fadb.h"
+
+namespace fadb {
+
+void set_error(const char* fmt, ...);
+
+#define FADB_CUDA_CHECK(expr)                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            ::fadb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FADB_E_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define FADB_CHECK(expr)            \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != FADB_OK) return _r; \
+    } while (0)
+
+#define FADB_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::fadb::set_error(__VA_ARGS__);     \
+            return FADB_E_INVALID;              \
+        }                                       \
+    } while (0)
+
+// device error codes written to handle->err_flag
+enum : int { DEVERR_NONE = 0, DEVERR_PIPE_TIMEOUT = 1, DEVERR_NONFINITE = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// A growable device buffer owned by the handle.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need) {
+        if (need <= bytes) return FADB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+            return FADB_E_NOMEM;
+        }
+        bytes = need;
+        return FADB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// A packed tensor-core layer: B operand [N][K] K-major bf16 (hi + lo planes) and fp32 bias.
+struct PackedLayer {
+    int N = 0, K = 0;      // K = taps * Cin
+    int Cin = 0, taps = 0;
+    __nv_bfloat16* w_hi = nullptr;
+    __nv_bfloat16* w_lo = nullptr;
+    float* bias = nullptr;   // [N] (folded BN shift or conv/linear bias)
+};
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    float* dev = nullptr;    // staging copy on device (fp32, PyTorch layout)
+    size_t numel = 0;
+};
+
+}  // namespace fadb
+
+// ------------------------------------------------------------------------------------------------
+struct fadb_handle {
+    int device = 0;
+    int sm_count = 148;
+    int precision = FADB_PREC_BF16;
+    int max_batch = 2048;           // VGGish patches per internal batch
+    int max_batch_cnn14 = 32;       // CNN14 clips per internal batch
+    int model = -1;                 // model whose weights are committed
+    bool weights_ready = false;
+    int64_t launches = 0;
+    int* err_flag = nullptr;        // device int
+    int* err_flag_host = nullptr;   // pinned mirror
+
+    std::map<std::string, fadb::HostTensor> staged;    // between weights_begin and commit
+    int staged_model = -1;
+
+    // first conv layer (Cin = 1): fp32 weights [9][64] (+BN folded), bias [64]; bn0 affine for CNN14
+    float* conv1_w = nullptr;
+    float* conv1_b = nullptr;
+    float* bn0_scale = nullptr;
+    float* bn0_shift = nullptr;
+    std::vector<fadb::PackedLayer> layers;             // tensor-core layers in execution order
+    fadb::DevBuf weight_pool;                          // backing store of all packed weights
+
+    // activation workspace
+    fadb::DevBuf ws_feats;      // fp32 features of one batch
+    fadb::DevBuf ws_act[2];     // ping-pong bf16 activations (hi plane followed by lo plane)
+    fadb::DevBuf ws_misc;       // pooled vectors etc.
+    fadb::DevBuf ws_frechet;    // fp64 workspace of fadb_frechet
+    fadb::DevBuf ws_stats;      // fp64 workspace of fadb_fad_from_pcm_host
+    fadb::DevBuf ws_pcm[2];     // double-buffered PCM chunks for the host path
+    fadb::DevBuf ws_emb;        // embeddings of the host path
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_compute[2] = {nullptr, nullptr};
+};
+
+namespace fadb {
+
+// ---- kernels / launchers implemented across the .cu files ---------------------------------------
+// frontend.cu
+int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips, int64_t n_samples,
+                    int64_t pcm_stride, float* feats, cudaStream_t st);
+int frontend_init(fadb_handle* h);
+
+int64_t frontend_rows(int model, int64_t n_samples);
+
+// conv1.cu — Cin = 1 direct 3x3 conv on CUDA cores
+int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, __nv_bfloat16* out_hi,
+                        __nv_bfloat16* out_lo, cudaStream_t st);
+int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int T, __nv_bfloat16* out_hi,
+                       __nv_bfloat16* out_lo, cudaStream_t st);
+
+// gemm_tc.cu — tcgen05 implicit-GEMM layer
+struct LayerIO {
+    const __nv_bfloat16* in_hi = nullptr;
+    const __nv_bfloat16* in_lo = nullptr;     // may be null (bf16 mode)
+    int B = 0, H = 0, W = 0, Cin = 0;          // NHWC input; a linear layer is B=1,H=1,W=rows
+    int taps = 9;                              // 9 = 3x3 pad 1, 1 = pointwise / linear
+    int relu = 1;
+    int pool = 0;                              // 0 none, 1 max 2x2, 2 avg 2x2
+    __nv_bfloat16* out_hi = nullptr;
+    __nv_bfloat16* out_lo = nullptr;           // may be null
+    float* out_f32 = nullptr;                  // if set, fp32 output instead of bf16
+};
+int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, cudaStream_t st);
+int gemm_init(fadb_handle* h);
+
+// pack.cu — weight repacking, BN folding, fp32 -> bf16 hi/lo split
+int pack_conv_weight(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
+                     __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, cudaStream_t st);
+int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                      cudaStream_t st);
+int fold_bn(fadb_handle* h, const float* gamma, const float* beta, const float* mean, const float* var, int C,
+            float* scale, float* shift, cudaStream_t st);
+
+// cnn14 tail (global pooling)  — cnn14.cu
+int launch_cnn14_global_pool(fadb_handle* h, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t B, int Ht,
+                             int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
+int launch_l2_normalize(fadb_handle* h, float* x, int64_t rows, int d, cudaStream_t st);
+
+// stats.cu
+int launch_stats_accumulate(fadb_handle* h, const float* emb, int64_t n, int d, int64_t ld, const double* shift,
+                            double* acc, cudaStream_t st);
+int launch_stats_accumulate_f64(fadb_handle* h, const double* emb, int64_t n, int d, int64_t ld, const double* shift,
+                                double* acc, cudaStream_t st);
+int launch_stats_finalize(fadb_handle* h, const double* acc, int d, const double* shift, double* mu, double* sigma,
+                          cudaStream_t st);
+
+// frechet.cu
+int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const double* mu2, const double* s2, int d,
+                   double* out, cudaStream_t st);
+
+}  // namespace fadb

@@ -1,0 +1,377 @@
+// frontend.cu — fused log-mel front-end kernel family (PCM -> framing -> window -> real FFT ->
+// |.| or |.|^2 -> sparse triangular mel projection -> log -> patch / time-padded layout), one warp
+// per STFT frame, everything between the PCM read and the feature write stays in shared memory.
+//
+// Replaces:
+//   VGGish : models/vggish.py:102-141 (_frame, _periodic_hann, _stft_magnitude), :150-190 (HTK mel
+//            matrix), :223-227 (log(mel + 0.01)), :268-277 (96-frame patches, trailing frames dropped)
+//   PANN   : models/pann.py:104-139 (librosa.stft centred/reflect, power, Slaney mel, 10 log10 max(.,1e-10)),
+//            fad.py:41-66 (zero rows up to T' = 32k-24)
+//   CLAP   : models/clap.py:70-72 (int16 truncation), fad.py:356-359 (zero-pad to 480000), fad.py:69-91
+//
+// Arithmetic: the FFT runs in fp64 like the reference (numpy promotes float32 PCM x float64 window
+// to float64; librosa evaluates the FFT in float64) — an fp32 FFT leaves a noise floor that breaks
+// 1e-5 log-mel parity on tonal inputs (empty bins sit at log(0.01)).  Real FFT of length NF as a
+// complex Stockham FFT of length NF/2 (radix-4 passes + one radix-2 pass when needed) + split.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace fadb {
+
+struct FrontTables {
+    double2* tw = nullptr;     // [NF]  exp(-2 pi i k / NF)
+    double* win = nullptr;     // [WIN] periodic Hann
+    int* band_start = nullptr; // [64]
+    int* band_len = nullptr;   // [64]
+    int* band_off = nullptr;   // [64]
+    double* band_w = nullptr;  // [sum len]
+    int nfft = 0, win_len = 0, hop = 0;
+    bool ready = false;
+};
+static FrontTables g_tables[5];   // per model; built per process (device-global, read-only)
+
+struct FrontParams {
+    const float* pcm;
+    long long pcm_stride;
+    int n_samples;      // samples physically present per clip
+    int logical_len;    // length used for reflect padding (CLAP: 480000)
+    int frames_valid;   // frames computed (rest of rows_out are zero rows)
+    int rows_out;       // rows written per clip
+    int hop, win_len;
+    int centered, power_db, quantize;
+    const double2* tw;
+    const double* win;
+    const int* band_start;
+    const int* band_len;
+    const int* band_off;
+    const double* band_w;
+    float* out;         // [n_clips][rows_out][64]
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) fadb_frontend_kernel(const FrontParams p) {
+    constexpr int M = NF / 2;
+    extern __shared__ __align__(16) uint8_t fsm[];
+    double2* s_tw = reinterpret_cast<double2*>(fsm);                       // [NF]
+    double* s_win = reinterpret_cast<double*>(fsm + NF * 16);              // [NF] (zero beyond win_len)
+    double2* s_buf = reinterpret_cast<double2*>(fsm + NF * 16 + NF * 8);   // [8 warps][2][M]
+
+    for (int i = threadIdx.x; i < NF; i += 256) {
+        s_tw[i] = p.tw[i];
+        s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* bufA = s_buf + warp * 2 * M;
+    double2* bufB = bufA + M;
+    const int clip = blockIdx.y;
+    const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
+    float* out = p.out + (size_t)clip * p.rows_out * 64;
+
+    for (int fi = 0; fi < 8; ++fi) {
+        const int row = blockIdx.x * 64 + warp * 8 + fi;
+        if (row >= p.rows_out) break;
+        if (row >= p.frames_valid) {                 // PANN time padding: literal zero rows (fad.py:61-64)
+            out[(size_t)row * 64 + lane] = 0.f;
+            out[(size_t)row * 64 + lane + 32] = 0.f;
+            continue;
+        }
+        // ---- load + window: z[n] = x[2n] + i x[2n+1]
+        const long long f0 = (long long)row * p.hop - (p.centered ? NF / 2 : 0);
+        for (int n = lane; n < M; n += 32) {
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 2 * n + e;
+                float s = 0.f;
+                if (j < p.win_len) {
+                    long long src = f0 + j;
+                    if (p.centered) {                // np.pad(mode='reflect'): edge sample not repeated
+                        if (src < 0) src = -src;
+                        if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
+                    }
+                    if (src >= 0 && src < p.n_samples) s = __ldg(pcm + src);
+                    if (p.quantize) {                // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
+                        const float q = truncf(__fmul_rn(s, 32767.0f));
+                        s = __fdiv_rn(q, 32767.0f);
+                    }
+                }
+                v[e] = (double)s * s_win[j];
+            }
+            bufA[n] = make_double2(v[0], v[1]);
+        }
+        __syncwarp();
+
+        // ---- complex Stockham FFT of length M (forward)
+        double2* x = bufA;
+        double2* y = bufB;
+        int pp = 1;
+        while (pp < M) {
+            const bool r4 = ((M / pp) % 4) == 0;
+            if (r4) {
+                const int T = M / 4;
+                const int tstep = NF / (pp * 4);
+                for (int i = lane; i < T; i += 32) {
+                    const int k = i & (pp - 1);
+                    double2 u0 = x[i];
+                    double2 u1 = cmul(x[i + T], s_tw[k * tstep]);
+                    double2 u2 = cmul(x[i + 2 * T], s_tw[2 * k * tstep]);
+                    double2 u3 = cmul(x[i + 3 * T], s_tw[3 * k * tstep]);
+                    const double2 v0 = make_double2(u0.x + u2.x, u0.y + u2.y);
+                    const double2 v1 = make_double2(u0.x - u2.x, u0.y - u2.y);
+                    const double2 v2 = make_double2(u1.x + u3.x, u1.y + u3.y);
+                    const double2 d = make_double2(u1.x - u3.x, u1.y - u3.y);
+                    const double2 v3 = make_double2(d.y, -d.x);          // -i * d
+                    const int j = (i - k) * 4 + k;
+                    y[j] = make_double2(v0.x + v2.x, v0.y + v2.y);
+                    y[j + pp] = make_double2(v1.x + v3.x, v1.y + v3.y);
+                    y[j + 2 * pp] = make_double2(v0.x - v2.x, v0.y - v2.y);
+                    y[j + 3 * pp] = make_double2(v1.x - v3.x, v1.y - v3.y);
+                }
+                pp *= 4;
+            } else {
+                const int T = M / 2;
+                const int tstep = NF / (pp * 2);
+                for (int i = lane; i < T; i += 32) {
+                    const int k = i & (pp - 1);
+                    const double2 u0 = x[i];
+                    const double2 u1 = cmul(x[i + T], s_tw[k * tstep]);
+                    const int j = (i - k) * 2 + k;
+                    y[j] = make_double2(u0.x + u1.x, u0.y + u1.y);
+                    y[j + pp] = make_double2(u0.x - u1.x, u0.y - u1.y);
+                }
+                pp *= 2;
+            }
+            __syncwarp();
+            double2* t = x; x = y; y = t;
+        }
+        // x holds Z[0..M); y is free -> spectrum as doubles spec[0..M]
+        double* spec = reinterpret_cast<double*>(y);
+        for (int k = lane; k <= M; k += 32) {
+            const double2 a = x[k & (M - 1)];
+            const double2 bz = x[(M - k) & (M - 1)];
+            const double2 b = make_double2(bz.x, -bz.y);                 // conj
+            const double2 ze = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+            const double2 dd = make_double2(a.x - b.x, a.y - b.y);       // (a-b)/(2i) = (dd.y - i dd.x)/2
+            const double2 zo = make_double2(0.5 * dd.y, -0.5 * dd.x);
+            const double2 w = s_tw[k];                                   // tw[M] = -1
+            const double2 X = make_double2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
+            double sv;
+            if (p.power_db) {                                            // complex64 -> |.| float32 -> ^2 (pann.py:118)
+                const float re = (float)X.x, im = (float)X.y;
+                const float mag = hypotf(re, im);
+                sv = (double)__fmul_rn(mag, mag);
+            } else {
+                sv = sqrt(X.x * X.x + X.y * X.y);                        // vggish.py:141
+            }
+            spec[k] = sv;
+        }
+        __syncwarp();
+        // ---- mel projection (sparse triangular bands) + log
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int b = lane + 32 * h2;
+            const int st = p.band_start[b], ln = p.band_len[b], off = p.band_off[b];
+            double acc = 0.0;
+            for (int i = 0; i < ln; ++i) acc = fma(__ldg(p.band_w + off + i), spec[st + i], acc);
+            float o;
+            if (p.power_db) {
+                const float m32 = fmaxf((float)acc, 1e-10f);
+                o = (float)(10.0 * log10((double)m32));                  // pann.py:133-134
+            } else {
+                o = (float)log(acc + 0.01);                              // vggish.py:227
+            }
+            out[(size_t)row * 64 + b] = o;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host: tables
+// ------------------------------------------------------------------------------------------------
+static const double kPi = 3.14159265358979323846;
+
+static void vggish_mel(int nbins, std::vector<std::vector<double>>& wcols) {
+    // models/vggish.py:150-190 : HTK mel, 64 bands 125..7500 Hz over linspace(0, 8000, 257), DC row zeroed
+    auto mel = [](double hz) { return 1127.0 * std::log(1.0 + hz / 700.0); };
+    const int nb = 64;
+    std::vector<double> binmel(nbins);
+    for (int k = 0; k < nbins; ++k) binmel[k] = mel(8000.0 * k / (nbins - 1));
+    const double lo = mel(125.0), hi = mel(7500.0);
+    std::vector<double> edges(nb + 2);
+    for (int i = 0; i < nb + 2; ++i) edges[i] = lo + (hi - lo) * i / (nb + 1);
+    wcols.assign(nb, std::vector<double>(nbins, 0.0));
+    for (int b = 0; b < nb; ++b) {
+        const double l = edges[b], c = edges[b + 1], u = edges[b + 2];
+        for (int k = 1; k < nbins; ++k) {
+            const double up = (binmel[k] - l) / (c - l), dn = (u - binmel[k]) / (u - c);
+            const double w = std::fmax(0.0, std::fmin(up, dn));
+            wcols[b][k] = w;
+        }
+    }
+}
+
+static void slaney_mel(int sr, int nfft, double fmin, double fmax, std::vector<std::vector<double>>& wcols) {
+    // semantics of librosa.filters.mel(htk=False, norm='slaney') as called at models/pann.py:121-127
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    auto h2m = [&](double hz) { return hz >= min_log_hz ? min_log_mel + std::log(hz / min_log_hz) / logstep : hz / f_sp; };
+    auto m2h = [&](double m) { return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m; };
+    const int nb = 64, nbins = nfft / 2 + 1;
+    std::vector<double> f(nb + 2);
+    const double ml = h2m(fmin), mh = h2m(fmax);
+    for (int i = 0; i < nb + 2; ++i) f[i] = m2h(ml + (mh - ml) * i / (nb + 1));
+    wcols.assign(nb, std::vector<double>(nbins, 0.0));
+    for (int b = 0; b < nb; ++b) {
+        const double enorm = 2.0 / (f[b + 2] - f[b]);
+        for (int k = 0; k < nbins; ++k) {
+            const double fk = (double)k * sr / nfft;
+            const double lower = (fk - f[b]) / (f[b + 1] - f[b]);
+            const double upper = (f[b + 2] - fk) / (f[b + 2] - f[b + 1]);
+            const double w = std::fmax(0.0, std::fmin(lower, upper)) * enorm;
+            wcols[b][k] = (double)(float)w;          // the reference filterbank is float32
+        }
+    }
+}
+
+static int build_tables(int model) {
+    FrontTables& t = g_tables[model];
+    if (t.ready) return FADB_OK;
+    int sr = 16000;
+    double fmin = 50, fmax = 8000;
+    switch (model) {
+        case FADB_MODEL_VGGISH: t.nfft = 512; t.win_len = 400; t.hop = 160; break;
+        case FADB_MODEL_PANN8K: t.nfft = 256; t.win_len = 256; t.hop = 80; sr = 8000; fmax = 4000; break;
+        case FADB_MODEL_PANN16K: t.nfft = 512; t.win_len = 512; t.hop = 160; sr = 16000; fmax = 8000; break;
+        case FADB_MODEL_PANN32K: t.nfft = 1024; t.win_len = 1024; t.hop = 320; sr = 32000; fmax = 14000; break;
+        case FADB_MODEL_CLAP: t.nfft = 1024; t.win_len = 1024; t.hop = 480; sr = 48000; fmax = 14000; break;
+        default: set_error("unknown model %d", model); return FADB_E_INVALID;
+    }
+    std::vector<double2> tw(t.nfft);
+    for (int k = 0; k < t.nfft; ++k) {
+        const double a = -2.0 * kPi * k / t.nfft;
+        tw[k] = make_double2(std::cos(a), std::sin(a));
+    }
+    std::vector<double> win(t.win_len);
+    for (int n = 0; n < t.win_len; ++n) win[n] = 0.5 - 0.5 * std::cos(2.0 * kPi / t.win_len * n);
+    std::vector<std::vector<double>> wc;
+    if (model == FADB_MODEL_VGGISH) vggish_mel(t.nfft / 2 + 1, wc);
+    else slaney_mel(sr, t.nfft, fmin, fmax, wc);
+    std::vector<int> bs(64), bl(64), bo(64);
+    std::vector<double> bw;
+    for (int b = 0; b < 64; ++b) {
+        int first = -1, last = -1;
+        for (int k = 0; k < (int)wc[b].size(); ++k)
+            if (wc[b][k] != 0.0) { if (first < 0) first = k; last = k; }
+        if (first < 0) { first = 0; last = -1; }
+        bs[b] = first; bl[b] = last - first + 1; bo[b] = (int)bw.size();
+        for (int k = first; k <= last; ++k) bw.push_back(wc[b][k]);
+    }
+    if (bw.empty()) bw.push_back(0.0);
+    FADB_CUDA_CHECK(cudaMalloc(&t.tw, tw.size() * sizeof(double2)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.win, win.size() * sizeof(double)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.band_start, 64 * sizeof(int)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.band_len, 64 * sizeof(int)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.band_off, 64 * sizeof(int)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.band_w, bw.size() * sizeof(double)));
+    FADB_CUDA_CHECK(cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.win, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.band_start, bs.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.band_len, bl.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.band_off, bo.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.band_w, bw.data(), bw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    t.ready = true;
+    return FADB_OK;
+}
+
+template <int NF>
+static constexpr int front_smem() { return NF * 16 + NF * 8 + 8 * 2 * (NF / 2) * 16; }
+
+int frontend_init(fadb_handle* h) {
+    (void)h;
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_frontend_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         front_smem<256>()));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_frontend_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         front_smem<512>()));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_frontend_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         front_smem<1024>()));
+    return FADB_OK;
+}
+
+static int64_t pann_pad(int64_t t) {        // fad.py:53-59
+    int64_t k = (t + 24 + 31) / 32;
+    int64_t v = 32 * k - 24;
+    if (v < t) v += 32;
+    return v;
+}
+
+// rows (patches for VGGish, frames T' otherwise) per clip
+int64_t frontend_rows(int model, int64_t n) {
+    switch (model) {
+        case FADB_MODEL_VGGISH: {
+            if (n < 400) return 0;
+            const int64_t f = 1 + (n - 400) / 160;
+            return f < 96 ? 0 : 1 + (f - 96) / 96;
+        }
+        case FADB_MODEL_PANN8K: return pann_pad(1 + n / 80);
+        case FADB_MODEL_PANN16K: return pann_pad(1 + n / 160);
+        case FADB_MODEL_PANN32K: return pann_pad(1 + n / 320);
+        case FADB_MODEL_CLAP: return 1001;
+        default: return -1;
+    }
+}
+
+int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips, int64_t n_samples,
+                    int64_t pcm_stride, float* feats, cudaStream_t st) {
+    FADB_REQUIRE(model >= 0 && model <= 4, "unknown model %d", model);
+    FADB_REQUIRE(n_samples > 0 && n_samples < (1LL << 30), "n_samples out of range");
+    FADB_CHECK(build_tables(model));
+    const FrontTables& t = g_tables[model];
+    if (n_clips <= 0) return FADB_OK;
+    FrontParams p;
+    p.pcm = pcm;
+    p.pcm_stride = pcm_stride;
+    p.n_samples = (int)n_samples;
+    p.logical_len = (int)n_samples;
+    p.hop = t.hop;
+    p.win_len = t.win_len;
+    p.centered = (model != FADB_MODEL_VGGISH);
+    p.power_db = (model != FADB_MODEL_VGGISH);
+    p.quantize = (model == FADB_MODEL_CLAP);
+    p.tw = t.tw; p.win = t.win;
+    p.band_start = t.band_start; p.band_len = t.band_len; p.band_off = t.band_off; p.band_w = t.band_w;
+    p.out = feats;
+    if (model == FADB_MODEL_VGGISH) {
+        const int64_t patches = frontend_rows(model, n_samples);
+        if (patches <= 0) return FADB_OK;
+        p.rows_out = (int)(patches * 96);
+        p.frames_valid = p.rows_out;
+    } else if (model == FADB_MODEL_CLAP) {
+        FADB_REQUIRE(n_samples <= 480000, "CLAP clips are at most 480000 samples (10 s), got %lld", (long long)n_samples);
+        p.logical_len = 480000;                       // fad.py:356-359 zero-pads the waveform first
+        p.rows_out = 1001;
+        p.frames_valid = 1001;
+    } else {
+        FADB_REQUIRE(n_samples > t.nfft / 2, "clip shorter than n_fft/2 cannot be reflect-padded");
+        p.frames_valid = (int)(1 + n_samples / t.hop);
+        p.rows_out = (int)pann_pad(p.frames_valid);
+    }
+    FADB_REQUIRE(n_clips <= 65535, "front end: at most 65535 clips per call");
+    dim3 grid((p.rows_out + 63) / 64, (unsigned)n_clips);
+    if (t.nfft == 256) fadb_frontend_kernel<256><<<grid, 256, front_smem<256>(), st>>>(p);
+    else if (t.nfft == 512) fadb_frontend_kernel<512><<<grid, 256, front_smem<512>(), st>>>(p);
+    else fadb_frontend_kernel<1024><<<grid, 256, front_smem<1024>(), st>>>(p);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+}  // namespace fadb

@@ -1,0 +1,589 @@
+// gemm_tc.cu — the tensor-core layer of the FAD hot path: 3x3 convolution (pad 1) and linear layers
+// as ONE persistent, warp-specialised tcgen05 implicit-GEMM kernel for sm_100a.
+//
+// Replaces the cuDNN/cuBLAS calls the reference reaches through nn.Conv2d / nn.Linear
+// (models/vggish.py:44-51,71-78; models/pann.py:161-176,234) — SURVEY.md §2.2 K7/K8/K9.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + tap offset, cin] * Wt[cout, tap, cin]
+//
+//   * A operand: NHWC bf16 activations.  A 4-D TMA tensor map (C, W, H, B) with box
+//     (64 ch, BW, BH, BB), BW*BH*BB = 128, lands one 128-pixel x 64-channel K-major SWIZZLE_128B
+//     tile per (tap, channel block); the 3x3 halo and the zero padding come for free from TMA
+//     out-of-bounds zero fill (coordinates start at x0-1 / y0-1).  No im2col buffer exists.
+//   * B operand: packed weights [Cout][tap][Cin] bf16 (K-major), 2-D tensor map, box (64, BN).
+//   * MMA: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN (64/128/256), K = 16, fp32
+//     accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+//   * split-bf16 ("bf16x3") mode: the K loop runs three passes (A_hi*B_hi, A_lo*B_hi, A_hi*B_lo)
+//     into the same accumulator, giving ~2^-16 relative operand precision with the same kernel.
+//   * Epilogue (4 warps): tcgen05.ld -> +bias (folded BN) -> ReLU -> fp32 staging tile in smem ->
+//     optional 2x2 max / avg pool -> bf16 hi(/lo) or fp32 NHWC, 16-byte stores.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fadb {
+
+// ------------------------------------------------------------------------------------------------
+// Kernel parameters (tensor maps live in the parameter/constant bank: __grid_constant__)
+// ------------------------------------------------------------------------------------------------
+struct GemmParams {
+    CUtensorMap tmA[2];   // activations hi, lo : dims (C, W, H, B)
+    CUtensorMap tmB[2];   // weights hi, lo     : dims (Ktot, N)
+    int W, H, B;
+    int BW, BH, BB;       // box; BW*BH*BB == 128
+    int tiles_w, tiles_h, tiles_b, tiles_n;
+    int num_tiles;
+    int cin_blocks;       // Cin / 64
+    int taps;             // 9 or 1
+    int npass;            // 1 (bf16) or 3 (bf16x3)
+    int N;                // Cout
+    int relu;
+    int pool;             // 0 none, 1 max, 2 avg
+    int Ho, Wo;           // output spatial dims (after pooling)
+    const float* bias;    // [N] or nullptr
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    float* out_f32;
+    int* err_flag;
+};
+
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                       // one 128-byte swizzle atom of bf16
+constexpr int kABytes = kTileM * kBlockK * 2;     // 16384
+constexpr int kStagePitch = 33;                   // fp32 staging row pitch (bank-conflict free)
+constexpr int kStagingBytes = kTileM * kStagePitch * 4;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);
+    static constexpr int kTmemCols = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + BN * 4 /*bias*/ + 256 /*barriers*/ +
+                                      1024 /*alignment slack*/;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a descriptor / pipeline bug must never hang the GPU.  ~2 s at 2 GHz, then trap.
+__device__ __noinline__ void mbar_timeout(int* err_flag, int code) {
+    if (err_flag) atomicExch(err_flag, code);
+    __threadfence_system();
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) mbar_timeout(err_flag, DEVERR_PIPE_TIMEOUT);
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, M = 128
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all MMAs previously issued by this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B (8 rows x 128 B) | layout type 2
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-B alignment
+    uint8_t* smem = smem_raw + (base - raw_addr);
+
+    float* staging = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+    float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + kStagingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + kStagingBytes + BN * 4);
+    const uint32_t bar_full = smem_u32(bars);                        // [kStages]
+    const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages]
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;              // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.tmA[0]);
+        prefetch_tmap(&p.tmB[0]);
+        if (p.npass > 1) {
+            prefetch_tmap(&p.tmA[1]);
+            prefetch_tmap(&p.tmB[1]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);                        // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nk = p.npass * p.taps * p.cin_blocks;                  // K blocks per tile
+    const int kb_per_pass = p.taps * p.cin_blocks;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int m = tile / p.tiles_n;
+                const int n0 = (tile - m * p.tiles_n) * BN;
+                const int wt = m % p.tiles_w; m /= p.tiles_w;
+                const int ht = m % p.tiles_h;
+                const int bt = m / p.tiles_h;
+                const int x0 = wt * p.BW, y0 = ht * p.BH, b0 = bt * p.BB;
+                for (int pass = 0; pass < p.npass; ++pass) {
+                    const CUtensorMap* ta = &p.tmA[pass == 1 ? 1 : 0];
+                    const CUtensorMap* tb = &p.tmB[pass == 2 ? 1 : 0];
+                    for (int kb = 0; kb < kb_per_pass; ++kb) {
+                        const int tap = kb / p.cin_blocks;
+                        const int cb = kb - tap * p.cin_blocks;
+                        int dy = 0, dx = 0;
+                        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
+                        const uint32_t sa = base + stage * Cfg::kStageBytes;
+                        const uint32_t sb = sa + kABytes;
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                        tma_load_2d(tb, bar_full + 8 * stage, sb, kb * kBlockK, n0);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                                       (uint32_t(kTileM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);    // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // TMA bytes landed
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * Cfg::kStageBytes;
+                    const uint64_t da = make_sw128_desc(sa);
+                    const uint64_t db = make_sw128_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty + 8 * stage);                     // frees the smem stage when MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(bar_tfull + 8 * as);                            // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================= epilogue =======================
+        const int ew = warp - 4;                     // TMEM lane quarter
+        const int et = threadIdx.x - 128;            // 0..127
+        const int row = ew * 32 + lane;              // accumulator row (= pixel within the tile)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            int m = tile / p.tiles_n;
+            const int n0 = (tile - m * p.tiles_n) * BN;
+            const int wt = m % p.tiles_w; m /= p.tiles_w;
+            const int ht = m % p.tiles_h;
+            const int bt = m / p.tiles_h;
+            const int x0 = wt * p.BW, y0 = ht * p.BH, b0 = bt * p.BB;
+
+            for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+
+            mbar_wait(bar_tfull + 8 * as, aphase, p.err_flag);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
+
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == BN / 32 - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+                }
+                epi_bar_sync();                      // previous chunk fully consumed (and bias_s visible)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float v = __uint_as_float(r[j]) + bias_s[c * 32 + j];
+                    if (p.relu) v = fmaxf(v, 0.f);
+                    staging[row * kStagePitch + j] = v;
+                }
+                epi_bar_sync();                      // staging tile complete
+
+                const int nb = n0 + c * 32;
+                if (p.pool == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int item = et + 128 * i;
+                        const int rr = item >> 2, g = item & 3;
+                        const int ww = rr % p.BW;
+                        const int t2 = rr / p.BW;
+                        const int hh = t2 % p.BH;
+                        const int bb = t2 / p.BH;
+                        const int x = x0 + ww, y = y0 + hh, b = b0 + bb;
+                        if (x < p.W && y < p.H && b < p.B) {
+                            const float* s = staging + rr * kStagePitch + g * 8;
+                            const size_t o = ((size_t(b) * p.Ho + y) * p.Wo + x) * p.N + nb + g * 8;
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = s[j];
+                            if (p.out_f32) {
+                                float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
+                                d[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                d[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            } else {
+                                uint4 hi;
+                                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                                *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
+                                if (p.out_lo) {
+                                    uint4 lo;
+                                    lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+                                    lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+                                    lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+                                    lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+                                    *reinterpret_cast<uint4*>(p.out_lo + o) = lo;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // 2x2 pooling inside the tile: 32 pooled pixels x 4 channel groups = 128 items
+                    const int pp = et >> 2, g = et & 3;
+                    const int hw = p.BW >> 1, hh2 = p.BH >> 1;
+                    const int pw = pp % hw;
+                    const int t2 = pp / hw;
+                    const int ph = t2 % hh2;
+                    const int pb = t2 / hh2;
+                    const int px = (x0 >> 1) + pw, py = (y0 >> 1) + ph, b = b0 + pb;
+                    if (px < p.Wo && py < p.Ho && b < p.B) {
+                        const int r00 = (pb * p.BH + 2 * ph) * p.BW + 2 * pw;
+                        const float* s0 = staging + r00 * kStagePitch + g * 8;
+                        const float* s1 = s0 + kStagePitch;
+                        const float* s2 = s0 + p.BW * kStagePitch;
+                        const float* s3 = s2 + kStagePitch;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (p.pool == 1) v[j] = fmaxf(fmaxf(s0[j], s1[j]), fmaxf(s2[j], s3[j]));
+                            else v[j] = ((s0[j] + s1[j]) + (s2[j] + s3[j])) * 0.25f;
+                        }
+                        const size_t o = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + nb + g * 8;
+                        if (p.out_f32) {
+                            float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
+                            d[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            d[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            uint4 hi;
+                            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                            *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
+                            if (p.out_lo) {
+                                uint4 lo;
+                                lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+                                lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+                                lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+                                lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+                                *reinterpret_cast<uint4*>(p.out_lo + o) = lo;
+                            }
+                        }
+                    }
+                }
+            }
+            epi_bar_sync();   // bias_s / staging free before the next tile overwrites them
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+int gemm_init(fadb_handle* h) {
+    (void)h;
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        FADB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled not available from the driver");
+            return FADB_E_CUDA;
+        }
+        g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<64>::kSmemBytes));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<128>::kSmemBytes));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<256>::kSmemBytes));
+    return FADB_OK;
+}
+
+static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(activations C=%d W=%d H=%d B=%d box %d,%d,%d) failed: %d", C, W, H, B, BW, BH,
+                  BB, (int)r);
+        return FADB_E_CUDA;
+    }
+    return FADB_OK;
+}
+
+static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weights K=%d N=%d BN=%d) failed: %d", K, N, BN, (int)r);
+        return FADB_E_CUDA;
+    }
+    return FADB_OK;
+}
+
+int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, cudaStream_t st) {
+    FADB_REQUIRE(g_encode != nullptr, "gemm layer used before gemm_init");
+    FADB_REQUIRE(io.Cin % kBlockK == 0, "Cin=%d must be a multiple of 64", io.Cin);
+    FADB_REQUIRE(io.Cin == L.Cin && io.taps == L.taps, "layer/IO mismatch (Cin %d vs %d, taps %d vs %d)", io.Cin,
+                 L.Cin, io.taps, L.taps);
+    FADB_REQUIRE(io.taps == 9 || io.taps == 1, "taps must be 1 or 9");
+    const int npass = (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3 : 1;
+    const int BN = (L.N % 256 == 0) ? 256 : (L.N % 128 == 0 ? 128 : 64);
+    FADB_REQUIRE(L.N % BN == 0 && L.N >= 64, "Cout=%d must be a multiple of 64", L.N);
+    FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
+
+    // pick the 128-pixel box: full rows first, then rows, then images
+    int BW = 1, BH = 1, BB = 1;
+    if (io.W >= kTileM || (io.taps == 1 && io.H == 1 && io.B == 1)) {
+        BW = kTileM;      // rows of a linear layer: the box may overhang the tensor, TMA zero-fills
+    } else {
+        BW = 1;
+        while (BW * 2 <= io.W && BW * 2 <= kTileM) BW *= 2;        // largest power of two <= W
+        FADB_REQUIRE(BW == io.W, "W=%d must be a power of two below 128 or >= 128", io.W);
+        BH = kTileM / BW;
+        if (BH > io.H) {
+            // fewer rows than the box: pick the power-of-two row count that wastes the fewest box rows
+            // (ties -> larger), and fill the rest of the 128 pixels with further images
+            int best = io.pool ? 2 : 1;
+            double best_waste = 1e30;
+            for (int c = best; c <= BH; c *= 2) {
+                const int tiles = (io.H + c - 1) / c;
+                const double waste = double(tiles) * c / io.H;
+                if (waste < best_waste - 1e-9 || (waste < best_waste + 1e-9 && c > best)) {
+                    best = c;
+                    best_waste = waste;
+                }
+            }
+            BH = best;
+            BB = kTileM / (BW * BH);
+        }
+    }
+    FADB_REQUIRE(BW * BH * BB == kTileM, "cannot tile W=%d H=%d into 128-pixel boxes", io.W, io.H);
+    if (io.pool) FADB_REQUIRE(BW % 2 == 0 && BH % 2 == 0, "pooling needs even box dims (BW=%d BH=%d)", BW, BH);
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB));
+    FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN));
+    if (npass == 3) {
+        FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB));
+        FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN));
+    } else {
+        p.tmA[1] = p.tmA[0];
+        p.tmB[1] = p.tmB[0];
+    }
+    p.W = io.W; p.H = io.H; p.B = io.B;
+    p.BW = BW; p.BH = BH; p.BB = BB;
+    p.tiles_w = (io.W + BW - 1) / BW;
+    p.tiles_h = (io.H + BH - 1) / BH;
+    p.tiles_b = (io.B + BB - 1) / BB;
+    p.tiles_n = L.N / BN;
+    const long long nt = 1LL * p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+    FADB_REQUIRE(nt < (1LL << 31), "too many tiles");
+    p.num_tiles = (int)nt;
+    p.cin_blocks = io.Cin / kBlockK;
+    p.taps = io.taps;
+    p.npass = npass;
+    p.N = L.N;
+    p.relu = io.relu;
+    p.pool = io.pool;
+    p.Ho = io.pool ? io.H / 2 : io.H;
+    p.Wo = io.pool ? io.W / 2 : io.W;
+    p.bias = L.bias;
+    p.out_hi = io.out_hi;
+    p.out_lo = (h->precision == FADB_PREC_BF16X3) ? io.out_lo : nullptr;
+    p.out_f32 = io.out_f32;
+    p.err_flag = h->err_flag;
+    FADB_REQUIRE(p.out_f32 || p.out_hi, "layer has no output buffer");
+
+    const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+    if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, GemmCfg<256>::kSmemBytes, st>>>(p);
+    else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, GemmCfg<128>::kSmemBytes, st>>>(p);
+    else fadb_gemm_tc_kernel<64><<<grid, kThreads, GemmCfg<64>::kSmemBytes, st>>>(p);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+}  // namespace fadb

@@ -1,0 +1,76 @@
+// pack.cu — weight repacking on the device: PyTorch layouts -> K-major bf16 (hi/lo planes) for the
+// tcgen05 B operand, eval-mode BatchNorm folding (models/pann.py:177-178,190-191; eps = 1e-5).
+#include "common.cuh"
+
+namespace fadb {
+
+// [Cout][Cin][k][k] fp32  ->  [Cout][tap = ky*k+kx][Cin] bf16 hi (+lo), optionally scaled per Cout
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
+                                        const float* __restrict__ scale, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo) {
+    const size_t total = size_t(Cout) * Cin * kk;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int ci = int(i % Cin);
+        const size_t t = i / Cin;
+        const int tap = int(t % kk);
+        const int co = int(t / kk);
+        float v = w[(size_t(co) * Cin + ci) * kk + tap];
+        if (scale) v *= scale[co];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+__global__ void split_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+__global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, int C,
+                               float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        const float s = gamma[c] / sqrtf(var[c] + 1e-5f);
+        scale[c] = s;
+        shift[c] = beta[c] - mean[c] * s;
+    }
+}
+
+static inline int grid_for(size_t n) {
+    size_t g = (n + 255) / 256;
+    return (int)(g > 4096 ? 4096 : (g ? g : 1));
+}
+
+int pack_conv_weight(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
+                     __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, cudaStream_t st) {
+    const size_t total = size_t(Cout) * Cin * ksize * ksize;
+    pack_conv_weight_kernel<<<grid_for(total), 256, 0, st>>>(w_oihw, Cout, Cin, ksize * ksize, scale, w_hi, w_lo);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                      cudaStream_t st) {
+    if (n <= 0) return FADB_OK;
+    split_kernel<<<grid_for((size_t)n), 256, 0, st>>>(x, (size_t)n, hi, lo);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+int fold_bn(fadb_handle* h, const float* gamma, const float* beta, const float* mean, const float* var, int C,
+            float* scale, float* shift, cudaStream_t st) {
+    fold_bn_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, C, scale, shift);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+}  // namespace fadb

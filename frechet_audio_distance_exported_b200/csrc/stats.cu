@@ -1,0 +1,163 @@
+// stats.cu — embedding statistics as a summable fp64 sufficient statistic.
+//
+// Replaces calculate_embd_statistics (fad.py:483-496: mu = np.mean, sigma = np.cov(rowvar=False), ddof = 1)
+// — SURVEY.md §2.2 K10.  acc = { n, sum (x-K), sum (x-K)(x-K)^T } in fp64 (K = optional common shift),
+// so partials from batches / GPUs add (NCCL allreduce between accumulate and finalize).
+// The d x d second moment is an fp64 DFMA syrk over 64x64 upper-triangular tiles, rows split across
+// CTAs, one fp64 atomicAdd flush per CTA tile.
+#include "common.cuh"
+
+namespace fadb {
+
+// ---------------------------------------------------------------- column sums + row count
+template <typename TIn>
+__global__ void __launch_bounds__(256) stats_colsum_kernel(const TIn* __restrict__ x, long long n, int d, long long ld,
+                                                           const double* __restrict__ shift, double* __restrict__ acc,
+                                                           int rows_per_cta) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta;
+    long long r1 = r0 + rows_per_cta;
+    if (r1 > n) r1 = n;
+    if (c < d && r0 < r1) {
+        const double k = shift ? shift[c] : 0.0;
+        double s = 0.0;
+        for (long long r = r0; r < r1; ++r) s += (double)__ldg(x + r * ld + c) - k;
+        atomicAdd(acc + 1 + c, s);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(acc, (double)n);
+}
+
+// ---------------------------------------------------------------- syrk: S += (X-K)^T (X-K), upper tiles
+constexpr int TS = 64;   // output tile
+constexpr int KC = 32;   // rows per smem chunk
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) stats_syrk_kernel(const TIn* __restrict__ x, long long n, int d, long long ld,
+                                                         const double* __restrict__ shift, double* __restrict__ S,
+                                                         int ntile, long long rows_per_cta) {
+    // decode upper-triangular tile pair
+    int pair = blockIdx.x, ti = 0;
+    while (pair >= ntile - ti) { pair -= ntile - ti; ++ti; }
+    const int tj = ti + pair;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta;
+    long long r1 = r0 + rows_per_cta;
+    if (r1 > n) r1 = n;
+    if (r0 >= r1) return;
+
+    __shared__ __align__(16) double sa[KC][TS];
+    __shared__ __align__(16) double sb[KC][TS];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4 x 4 outputs each
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    const int ci0 = ti * TS, cj0 = tj * TS;
+    for (long long rb = r0; rb < r1; rb += KC) {
+        // stage KC rows of both column tiles as (x - K) in fp64; out-of-range -> 0
+        for (int e = threadIdx.x; e < KC * TS; e += 256) {
+            const int rr = e / TS, cc = e % TS;
+            const long long r = rb + rr;
+            double va = 0.0, vb = 0.0;
+            if (r < r1) {
+                if (ci0 + cc < d) va = (double)__ldg(x + r * ld + ci0 + cc) - (shift ? shift[ci0 + cc] : 0.0);
+                if (cj0 + cc < d) vb = (double)__ldg(x + r * ld + cj0 + cc) - (shift ? shift[cj0 + cc] : 0.0);
+            }
+            sa[rr][cc] = va;
+            sb[rr][cc] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < KC; ++k) {
+            const double2 a01 = *reinterpret_cast<const double2*>(&sa[k][ty * 4]);
+            const double2 a23 = *reinterpret_cast<const double2*>(&sa[k][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2*>(&sb[k][tx * 4]);
+            const double2 b23 = *reinterpret_cast<const double2*>(&sb[k][tx * 4 + 2]);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+            const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gi = ci0 + ty * 4 + i, gj = cj0 + tx * 4 + j;
+            if (gi < d && gj < d) atomicAdd(S + (size_t)gi * d + gj, acc[i][j]);
+        }
+}
+
+// ---------------------------------------------------------------- finalize
+__global__ void stats_finalize_kernel(const double* __restrict__ acc, int d, const double* __restrict__ shift,
+                                      double* __restrict__ mu, double* __restrict__ sigma) {
+    const double n = acc[0];
+    const double* s1 = acc + 1;
+    const double* S = acc + 1 + d;
+    const size_t total = (size_t)d * d;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / d), j = (int)(e % d);
+        const double sij = (i / TS <= j / TS) ? S[(size_t)i * d + j] : S[(size_t)j * d + i];
+        const double di = s1[i] / n, dj = s1[j] / n;
+        sigma[e] = (sij - n * di * dj) / (n - 1.0);
+        if (j == 0 && mu) mu[i] = (shift ? shift[i] : 0.0) + di;
+    }
+}
+
+template <typename TIn>
+static int stats_accumulate_t(fadb_handle* h, const TIn* emb, int64_t n, int d, int64_t ld, const double* shift,
+                              double* acc, cudaStream_t st) {
+    FADB_REQUIRE(d > 0 && d <= 8192, "embedding dim %d out of range", d);
+    FADB_REQUIRE(ld >= d, "row stride %lld < d", (long long)ld);
+    if (n <= 0) return FADB_OK;
+    {
+        int rows_per = 1024;
+        long long ny = (n + rows_per - 1) / rows_per;
+        while (ny > 32768) { rows_per *= 2; ny = (n + rows_per - 1) / rows_per; }
+        dim3 grid((d + 255) / 256, (unsigned)ny);
+        stats_colsum_kernel<TIn><<<grid, 256, 0, st>>>(emb, n, d, ld, shift, acc, rows_per);
+        h->launches++;
+    }
+    {
+        const int ntile = (d + TS - 1) / TS;
+        const int npair = ntile * (ntile + 1) / 2;
+        long long want = (4LL * h->sm_count + npair - 1) / npair;           // row splits to fill the machine
+        long long rows_per = (n + want - 1) / want;
+        if (rows_per < 256) rows_per = 256;
+        rows_per = (rows_per + KC - 1) / KC * KC;
+        long long ny = (n + rows_per - 1) / rows_per;
+        while (ny > 32768) { rows_per *= 2; ny = (n + rows_per - 1) / rows_per; }
+        dim3 grid(npair, (unsigned)ny);
+        stats_syrk_kernel<TIn><<<grid, 256, 0, st>>>(emb, n, d, ld, shift, acc + 1 + d, ntile, rows_per);
+        h->launches++;
+    }
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+int launch_stats_accumulate(fadb_handle* h, const float* emb, int64_t n, int d, int64_t ld, const double* shift,
+                            double* acc, cudaStream_t st) {
+    return stats_accumulate_t<float>(h, emb, n, d, ld, shift, acc, st);
+}
+int launch_stats_accumulate_f64(fadb_handle* h, const double* emb, int64_t n, int d, int64_t ld, const double* shift,
+                                double* acc, cudaStream_t st) {
+    return stats_accumulate_t<double>(h, emb, n, d, ld, shift, acc, st);
+}
+
+int launch_stats_finalize(fadb_handle* h, const double* acc, int d, const double* shift, double* mu, double* sigma,
+                          cudaStream_t st) {
+    FADB_REQUIRE(d > 0 && d <= 8192, "embedding dim %d out of range", d);
+    size_t total = (size_t)d * d;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 2048) grid = 2048;
+    stats_finalize_kernel<<<grid, 256, 0, st>>>(acc, d, shift, mu, sigma);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+}  // namespace fadb

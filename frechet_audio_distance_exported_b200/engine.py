@@ -1,0 +1,192 @@
+"""Thin torch-facing wrapper over the C ABI (include/fadb.h).  PyTorch is only plumbing here: device
+memory, streams and torch.distributed; all arithmetic is in libfadb200.so.
+
+One `Engine` = one fadb_handle on one GPU with one model's weights committed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODEL_IDS, PREC_IDS, check
+
+SAMPLE_RATES = {"vggish": 16000, "pann-8k": 8000, "pann-16k": 16000, "pann-32k": 32000, "clap": 48000}
+EMBED_DIMS = {"vggish": 128, "pann-8k": 2048, "pann-16k": 2048, "pann-32k": 2048, "clap": 512}
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("frechet_audio_distance_exported_b200 needs a B200 GPU: there is no CPU fallback")
+
+
+def _stream_ptr() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, model_name: str, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 precision: str = "bf16", device: Optional[int] = None, max_batch: Optional[int] = None):
+        if model_name not in MODEL_IDS:
+            raise ValueError(f"Unknown model: {model_name}. Valid options: {list(MODEL_IDS)}")
+        _require_cuda()
+        self.lib = _lib.load()
+        self.model_name = model_name
+        self.model_id = MODEL_IDS[model_name]
+        self.sample_rate = SAMPLE_RATES[model_name]
+        self.dim = EMBED_DIMS[model_name]
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.handle = _lib.Handle(self.device_index)
+        self.h = self.handle.ptr
+        self.set_precision(precision)
+        if max_batch is not None:
+            check(self.lib.fadb_set_max_batch(self.h, int(max_batch)))
+        self.weights_loaded = False
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------ configuration
+    def set_precision(self, precision: str) -> None:
+        if precision not in PREC_IDS:
+            raise ValueError(f"precision must be one of {list(PREC_IDS)}")
+        check(self.lib.fadb_set_precision(self.h, PREC_IDS[precision]))
+        self.precision = precision
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Hand the reference modules' state_dict (VGGishCore / PANNCore key names) to the packer."""
+        check(self.lib.fadb_weights_begin(self.h, self.model_id))
+        for name, t in sd.items():
+            if not torch.is_tensor(t) or not t.is_floating_point():
+                continue                                  # num_batches_tracked etc.
+            a = t.detach().to("cpu", torch.float32).contiguous()
+            shape = (C.c_int64 * max(a.dim(), 1))(*a.shape)
+            check(self.lib.fadb_weights_tensor(self.h, name.encode(), C.c_void_p(a.data_ptr()), shape, a.dim()))
+        check(self.lib.fadb_weights_commit(self.h))
+        self.weights_loaded = True
+
+    # ------------------------------------------------------------------ hot path pieces (device tensors)
+    def frontend_rows(self, n_samples: int) -> int:
+        return int(self.lib.fadb_frontend_rows(self.model_id, int(n_samples)))
+
+    def frontend(self, pcm: torch.Tensor) -> torch.Tensor:
+        """pcm [n_clips, n_samples] fp32 cuda -> VGGish [n_clips*P, 96, 64] / CNN14 [n_clips, T', 64] fp32."""
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.dim() == 2 and pcm.stride(1) == 1
+        n_clips, n = pcm.shape
+        rows = self.frontend_rows(n)
+        if self.model_id == 0:
+            out = torch.empty((n_clips * max(rows, 0), 96, 64), dtype=torch.float32, device=pcm.device)
+        else:
+            out = torch.empty((n_clips, rows, 64), dtype=torch.float32, device=pcm.device)
+        if out.numel():
+            check(self.lib.fadb_frontend(self.h, self.model_id, _p(pcm), n_clips, n, pcm.stride(0), _p(out),
+                                         C.c_void_p(_stream_ptr())))
+        return out
+
+    def embed_features(self, feats: torch.Tensor) -> torch.Tensor:
+        """feats [items, T, 64] fp32 cuda -> [items, d] fp32 (the reference's `self.model(x)`)."""
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 3 and feats.shape[2] == 64
+        feats = feats.contiguous()
+        out = torch.empty((feats.shape[0], self.dim), dtype=torch.float32, device=feats.device)
+        if feats.shape[0]:
+            check(self.lib.fadb_embed(self.h, _p(feats), feats.shape[0], feats.shape[1], _p(out),
+                                      C.c_void_p(_stream_ptr())))
+        return out
+
+    def embed_pcm(self, pcm: torch.Tensor) -> torch.Tensor:
+        """pcm [n_clips, n_samples] fp32 cuda -> embeddings [rows, d] fp32 (front end + network)."""
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.dim() == 2 and pcm.stride(1) == 1
+        n_clips, n = pcm.shape
+        rows = self.frontend_rows(n) if self.model_id == 0 else 1
+        out = torch.empty((n_clips * max(rows, 0), self.dim), dtype=torch.float32, device=pcm.device)
+        if out.numel():
+            check(self.lib.fadb_embed_pcm(self.h, _p(pcm), n_clips, n, pcm.stride(0), _p(out),
+                                          C.c_void_p(_stream_ptr())))
+        return out
+
+    # ------------------------------------------------------------------ statistics
+    def new_acc(self, d: Optional[int] = None) -> torch.Tensor:
+        d = self.dim if d is None else d
+        return torch.zeros(1 + d + d * d, dtype=torch.float64, device=self.device)
+
+    def stats_accumulate(self, emb: torch.Tensor, acc: torch.Tensor, shift: Optional[torch.Tensor] = None) -> None:
+        assert emb.is_cuda and emb.dim() == 2 and emb.stride(1) == 1
+        d = emb.shape[1]
+        assert acc.numel() == 1 + d + d * d and acc.dtype == torch.float64
+        if emb.shape[0] == 0:
+            return
+        fn = self.lib.fadb_stats_accumulate if emb.dtype == torch.float32 else self.lib.fadb_stats_accumulate_f64
+        assert emb.dtype in (torch.float32, torch.float64)
+        check(fn(self.h, _p(emb), emb.shape[0], d, emb.stride(0), _p(shift), _p(acc), C.c_void_p(_stream_ptr())))
+
+    def stats_finalize(self, acc: torch.Tensor, d: int, shift: Optional[torch.Tensor] = None):
+        mu = torch.empty(d, dtype=torch.float64, device=acc.device)
+        sigma = torch.empty((d, d), dtype=torch.float64, device=acc.device)
+        check(self.lib.fadb_stats_finalize(self.h, _p(acc), d, _p(shift), _p(mu), _p(sigma), C.c_void_p(_stream_ptr())))
+        return mu, sigma
+
+    def allreduce_acc(self, acc: torch.Tensor, group=None) -> None:
+        """The only collective of the path: one NCCL all-reduce (sum, fp64) of {n, sum x, sum x x^T}."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+
+    # ------------------------------------------------------------------ Frechet
+    def frechet(self, mu1, sigma1, mu2, sigma2) -> torch.Tensor:
+        """device fp64 tensors -> device fp64[4] = {fad, tr sqrt(S1 S2), tr S1 + tr S2, |mu1-mu2|^2}."""
+        d = mu1.numel()
+        for t in (mu1, sigma1, mu2, sigma2):
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        out = torch.empty(4, dtype=torch.float64, device=mu1.device)
+        check(self.lib.fadb_frechet(self.h, _p(mu1), _p(sigma1), _p(mu2), _p(sigma2), d, _p(out),
+                                    C.c_void_p(_stream_ptr())))
+        return out
+
+    # ------------------------------------------------------------------ whole path, host buffers
+    def fad_from_pcm_host(self, pcm_bg: torch.Tensor, pcm_ev: torch.Tensor, return_embeddings: bool = False):
+        """pcm_* : [n_clips, n_samples] fp32 HOST tensors (pinned recommended).  One C call: chunked H2D
+        overlapped with compute, statistics, Frechet, scalar D2H."""
+        for t in (pcm_bg, pcm_ev):
+            assert (not t.is_cuda) and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()
+        assert pcm_bg.shape[1] == pcm_ev.shape[1]
+        n = pcm_bg.shape[1]
+        rows = self.frontend_rows(n) if self.model_id == 0 else 1
+        eb = ee = None
+        if return_embeddings:
+            eb = torch.empty((pcm_bg.shape[0] * rows, self.dim), dtype=torch.float32).pin_memory()
+            ee = torch.empty((pcm_ev.shape[0] * rows, self.dim), dtype=torch.float32).pin_memory()
+        out = C.c_double(0.0)
+        check(self.lib.fadb_fad_from_pcm_host(self.h, _p(pcm_bg), pcm_bg.shape[0], _p(pcm_ev), pcm_ev.shape[0], n,
+                                              _p(eb), _p(ee), C.byref(out)))
+        if return_embeddings:
+            return out.value, eb.numpy(), ee.numpy()
+        return out.value
+
+    def launch_count(self) -> int:
+        return self.handle.launch_count()
+
+    def device_status(self) -> int:
+        return int(self.lib.fadb_device_status(self.h))
+
+    # ------------------------------------------------------------------ test hook
+    def debug_conv_layer(self, x_nhwc: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
+                         relu: bool, pool: int) -> torch.Tensor:
+        B, H, W, Cin = x_nhwc.shape
+        Cout = w.shape[0]
+        Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+        out = torch.zeros((B, Ho, Wo, Cout), dtype=torch.float32, device=x_nhwc.device)
+        check(self.lib.fadb_debug_conv_layer(self.h, _p(x_nhwc.contiguous()), B, H, W, Cin, _p(w.contiguous()),
+                                             _p(bias), Cout, ksize, int(relu), int(pool), _p(out),
+                                             C.c_void_p(_stream_ptr())))
+        return out
+
+
+def embeddings_to_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to("cpu").numpy()

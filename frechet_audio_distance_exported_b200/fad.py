@@ -1,0 +1,350 @@
+"""Drop-in façade: same class, method names, argument meaning and error behaviour as the reference
+`frechet_audio_distance_exported.fad.FrechetAudioDistance` (fad.py:164-662), with the hot path
+(PCM -> log-mel -> VGGish / CNN14 embedding -> mean/cov -> Frechet) running in libfadb200.so on a
+B200.  There is no CPU fallback.
+
+Differences a user of the reference sees:
+  * weights: the reference downloads `*.pt2` artefacts (fad.py:249-300); offline we accept a
+    state_dict of the reference's own modules (`state_dict=` or a file in `ckpt_dir`);
+  * "clap" is the CNN14 audio branch + projection head (BASELINE.json / README of the reference),
+    not the HTSAT artefact; "encodec-*" is out of scope and raises NotImplementedError;
+  * resampling (resampy) is not built yet: non-native-rate input raises and, inside
+    get_embeddings / score, is handled like any per-clip error of the reference (skipped / -1).
+"""
+from __future__ import annotations
+
+import os
+from multiprocessing.dummy import Pool as ThreadPool
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+CLAP_TIME_FRAMES = 1001                       # fad.py:38
+
+# fad.py:109-117
+VALID_MODELS = {
+    "vggish": {"sample_rate": 16000, "embedding_dim": 128},
+    "pann-8k": {"sample_rate": 8000, "embedding_dim": 2048},
+    "pann-16k": {"sample_rate": 16000, "embedding_dim": 2048},
+    "pann-32k": {"sample_rate": 32000, "embedding_dim": 2048},
+    "encodec-24k": {"sample_rate": 24000, "embedding_dim": 128, "channels": 1},
+    "encodec-48k": {"sample_rate": 48000, "embedding_dim": 128, "channels": 2},
+    "clap": {"sample_rate": 48000, "embedding_dim": 512},
+}
+PANN_SAMPLE_RATES = {"pann-8k": 8000, "pann-16k": 16000, "pann-32k": 32000}        # fad.py:120-124
+ENCODEC_SAMPLE_RATES = {"encodec-24k": 24000, "encodec-48k": 48000}               # fad.py:127-130
+# fad.py:95-106 — kept for API compatibility; nothing is downloaded (no network on the GPU boxes)
+EXPORTED_MODEL_URLS = {
+    "vggish": "https://github.com/gibiansky/frechet-audio-distance-exported/releases/download/v0.1/vggish_exported.pt2",
+    "pann-8k": "https://github.com/gibiansky/frechet-audio-distance-exported/releases/download/v0.2/pann_cnn14_8k_exported.pt2",
+    "pann-16k": "https://github.com/gibiansky/frechet-audio-distance-exported/releases/download/v0.2/pann_cnn14_16k_exported.pt2",
+    "pann-32k": "https://github.com/gibiansky/frechet-audio-distance-exported/releases/download/v0.2/pann_cnn14_32k_exported.pt2",
+    "clap": "https://github.com/gibiansky/frechet-audio-distance-exported/releases/download/v0.3/clap_exported.pt2",
+}
+
+
+def _pad_to_valid_pann_time(x: torch.Tensor) -> torch.Tensor:
+    """fad.py:41-66 — kept for callers that feed `model(x)` themselves; the fused front end already
+    emits the padded layout."""
+    time = x.shape[2]
+    k = (time + 24 + 31) // 32
+    valid_time = 32 * k - 24
+    if valid_time < time:
+        valid_time += 32
+    if valid_time > time:
+        x = torch.nn.functional.pad(x, (0, 0, 0, valid_time - time))
+    return x
+
+
+def _pad_to_clap_time(x: torch.Tensor) -> torch.Tensor:
+    """fad.py:69-91."""
+    time = x.shape[2]
+    if time < CLAP_TIME_FRAMES:
+        x = torch.nn.functional.pad(x, (0, 0, 0, CLAP_TIME_FRAMES - time))
+    elif time > CLAP_TIME_FRAMES:
+        x = x[:, :, :CLAP_TIME_FRAMES, :]
+    return x
+
+
+def load_audio(fname: str, sample_rate: int, channels: int, dtype: str = "float32") -> np.ndarray:
+    """fad.py:133-161 for RIFF/WAV files (PCM 8/16/24/32-bit and IEEE float), without libsndfile."""
+    from scipy.io import wavfile
+
+    sr, raw = wavfile.read(fname)
+    if raw.dtype == np.uint8:
+        f = (raw.astype(np.float64) - 128.0) / 128.0
+    elif raw.dtype == np.int16:
+        f = raw.astype(np.float64) / 32768.0
+    elif raw.dtype == np.int32:                      # 24-bit is left-justified in int32 by scipy
+        f = raw.astype(np.float64) / 2147483648.0
+    else:
+        f = raw.astype(np.float64)
+    if dtype == "int16":                              # fad.py:148-149 (sf.read int16, then / 32768.0)
+        wav_data = np.clip(np.round(f * 32768.0), -32768, 32767).astype(np.int16) / 32768.0
+    elif dtype == "int32":                            # fad.py:150-151
+        wav_data = np.clip(np.round(f * 2147483648.0), -2147483648, 2147483647).astype(np.int32) / float(2 ** 31)
+    else:
+        wav_data = f.astype(dtype)
+    if len(wav_data.shape) > channels:                # fad.py:154-155
+        wav_data = np.mean(wav_data, axis=1)
+    if sr != sample_rate:                             # fad.py:158-159
+        raise NotImplementedError(
+            f"{fname}: sample rate {sr} != {sample_rate}; the resampy-equivalent resampler is not built yet")
+    return wav_data
+
+
+class _B200Model:
+    """Callable with the contract of the reference's `self.model` (fad.py:297-299):
+    [B,1,96,64] -> [B,128]; [B,1,T,64] -> [B,2048]; [B,1,1001,64] -> [B,512]; fp32 torch tensors."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.shape[1] != 1 or x.shape[3] != 64:
+            raise ValueError(f"expected [B,1,T,64], got {tuple(x.shape)}")
+        x = x.to(self.engine.device, torch.float32)
+        return self.engine.embed_features(x[:, 0].contiguous())
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+
+class FrechetAudioDistance:
+    """API-compatible FAD calculator (reference fad.py:164-662) on libfadb200.so."""
+
+    def __init__(
+        self,
+        ckpt_dir: Optional[str] = None,
+        model_name: str = "vggish",
+        sample_rate: Optional[int] = None,
+        channels: int = 1,
+        verbose: bool = False,
+        audio_load_worker: int = 8,
+        *,
+        state_dict: Optional[Dict[str, torch.Tensor]] = None,
+        precision: str = "bf16",
+        process_group=None,
+    ):
+        if model_name not in VALID_MODELS:                                     # fad.py:205-208
+            raise ValueError(f"Unknown model: {model_name}. Valid options: {list(VALID_MODELS.keys())}")
+        expected_sr = VALID_MODELS[model_name]["sample_rate"]
+        if sample_rate is None:                                                # fad.py:214-219
+            sample_rate = expected_sr
+        elif sample_rate != expected_sr:
+            raise ValueError(f"Model '{model_name}' requires sample_rate={expected_sr}, got {sample_rate}")
+        self.model_name = model_name
+        self.sample_rate = sample_rate
+        self.channels = channels
+        self.verbose = verbose
+        self.audio_load_worker = audio_load_worker
+        self.precision = precision
+        self.process_group = process_group
+        if not torch.cuda.is_available():                                      # fad.py:228-233, minus mps/cpu
+            raise RuntimeError("frechet_audio_distance_exported_b200 needs a B200 GPU: there is no CPU fallback")
+        self.device = torch.device("cuda")
+        if self.verbose:
+            print(f"[Exported FAD] Using device: {self.device}")
+        if ckpt_dir is not None:                                               # fad.py:239-244
+            os.makedirs(ckpt_dir, exist_ok=True)
+            self.ckpt_dir = ckpt_dir
+        else:
+            self.ckpt_dir = os.path.join(torch.hub.get_dir(), "exported_fad")
+            os.makedirs(self.ckpt_dir, exist_ok=True)
+        self._state_dict = state_dict
+        self._load_model()
+
+    # ------------------------------------------------------------------ fad.py:249-300
+    def _model_filename(self) -> str:
+        if self.model_name == "vggish":
+            return "vggish_exported.pt2"
+        if self.model_name in PANN_SAMPLE_RATES:
+            return f"pann_cnn14_{self.model_name.split('-')[1]}_exported.pt2"
+        if self.model_name == "clap":
+            return "clap_exported.pt2"
+        return f"{self.model_name}_exported.pt2"
+
+    def _load_model(self):
+        if self.model_name in ENCODEC_SAMPLE_RATES:
+            raise NotImplementedError("Encodec is out of scope of the B200 hot path (no model source in the reference)")
+        sd = self._state_dict
+        if sd is None:
+            path = os.path.join(self.ckpt_dir, self._model_filename())
+            alt = os.path.splitext(path)[0] + "_state_dict.pt"
+            if os.path.exists(path):
+                if self.verbose:
+                    print(f"[Exported FAD] Loading model from {path}...")
+                sd = dict(torch.export.load(path).state_dict)                  # fad.py:297
+            elif os.path.exists(alt):
+                sd = torch.load(alt, map_location="cpu")
+            else:
+                raise FileNotFoundError(
+                    f"Exported model not found at {path} (or {alt}) and downloading is unavailable offline. "
+                    f"Pass state_dict= or provide a valid ckpt_dir.")
+        self.engine = Engine(self.model_name, sd, precision=self.precision)
+        self.model = _B200Model(self.engine)
+
+    # ------------------------------------------------------------------ fad.py:302-408
+    def _prepare_clip(self, audio: np.ndarray, sr: int) -> np.ndarray:
+        audio = np.asarray(audio)
+        if audio.ndim > 1:                                                     # vggish.py:245-246 / pann.py:96-97
+            audio = np.mean(audio, axis=1)
+        if sr != self.sample_rate:                                             # vggish.py:249-250 / pann.py:100-101
+            raise NotImplementedError("resampling is not built yet")
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        if self.model_name == "clap" and audio.shape[0] > 480000:
+            raise ValueError("CLAP clips are limited to 10 s")
+        if self.model_name != "vggish" and self.model_name != "clap":
+            n_fft = {8000: 256, 16000: 512, 32000: 1024}[self.sample_rate]
+            if audio.shape[0] <= n_fft // 2:
+                raise ValueError("clip too short for reflect padding")
+        return audio
+
+    def get_embeddings(self, x: List[np.ndarray], sr: int) -> np.ndarray:
+        """Embeddings for a list of clips, concatenated in input order.  Clips of equal length are
+        batched into one device call (the reference loops clip by clip, fad.py:317)."""
+        prepared = []
+        for audio in x:
+            try:
+                prepared.append(self._prepare_clip(audio, sr))
+            except Exception as e:                                             # fad.py:400-403
+                if self.verbose:
+                    print(f"[Exported FAD] Error processing audio: {e}")
+                prepared.append(None)
+        by_len: Dict[int, List[int]] = {}
+        for i, a in enumerate(prepared):
+            if a is not None:
+                by_len.setdefault(a.shape[0], []).append(i)
+        results: Dict[int, np.ndarray] = {}
+        for n, idxs in by_len.items():
+            try:
+                rows = self.engine.frontend_rows(n) if self.model_name == "vggish" else 1
+                if rows <= 0:
+                    for i in idxs:
+                        results[i] = np.zeros((0, self.engine.dim), dtype=np.float32)
+                    continue
+                host = torch.from_numpy(np.stack([prepared[i] for i in idxs]))
+                emb = self.engine.embed_pcm(host.to(self.device, non_blocking=False)).cpu().numpy()
+                for j, i in enumerate(idxs):
+                    results[i] = emb[j * rows:(j + 1) * rows]
+            except Exception as e:
+                if self.verbose:
+                    print(f"[Exported FAD] Error processing audio: {e}")
+        embd_lst = [results[i] for i in range(len(prepared)) if i in results]
+        if not embd_lst:
+            return np.array([])                                                # fad.py:405-406
+        return np.concatenate(embd_lst, axis=0)                                # fad.py:408
+
+    def _get_embedding_for_audio(self, audio: np.ndarray) -> np.ndarray:
+        """fad.py:410-481."""
+        a = self._prepare_clip(audio, self.sample_rate)
+        return self.engine.embed_pcm(torch.from_numpy(a)[None].to(self.device)).cpu().numpy()
+
+    # ------------------------------------------------------------------ fad.py:483-496
+    def calculate_embd_statistics(self, embd_lst):
+        if isinstance(embd_lst, list):
+            embd_lst = np.array(embd_lst)
+        embd_lst = np.asarray(embd_lst)
+        in_dtype = embd_lst.dtype
+        work = torch.float64 if in_dtype == np.float64 else torch.float32
+        e = torch.from_numpy(np.ascontiguousarray(embd_lst)).to(self.device, work)
+        eng = self.engine
+        d = e.shape[1]
+        acc = eng.new_acc(d)
+        eng.stats_accumulate(e, acc)
+        mu, sigma = eng.stats_finalize(acc, d)
+        mu_np = mu.cpu().numpy()
+        if in_dtype != np.float64:
+            mu_np = mu_np.astype(np.float32)        # np.mean of float32 embeddings is float32
+        return mu_np, sigma.cpu().numpy()
+
+    # ------------------------------------------------------------------ fad.py:498-555
+    def calculate_frechet_distance(self, mu1, sigma1, mu2, sigma2, eps: float = 1e-6) -> float:
+        mu1 = np.atleast_1d(mu1)
+        mu2 = np.atleast_1d(mu2)
+        sigma1 = np.atleast_2d(sigma1)
+        sigma2 = np.atleast_2d(sigma2)
+        assert mu1.shape == mu2.shape, "Training and test mean vectors have different lengths"
+        assert sigma1.shape == sigma2.shape, "Training and test covariances have different dimensions"
+        dev = self.device
+        t = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev) for a in (mu1, sigma1, mu2, sigma2)]
+        out = self.engine.frechet(*t).cpu().numpy()
+        if not np.isfinite(out[0]):
+            raise ValueError("Frechet distance is not finite")
+        return np.float64(out[0])
+
+    # ------------------------------------------------------------------ fad.py:557-591
+    def _load_audio_files(self, dir: str, dtype: str = "float32") -> List[np.ndarray]:
+        pool = ThreadPool(self.audio_load_worker)
+        files = [f for f in os.listdir(dir) if not f.startswith(".")]
+        if self.verbose:
+            print(f"[Exported FAD] Loading audio from {dir}...")
+        tasks = [pool.apply_async(load_audio, args=(os.path.join(dir, f), self.sample_rate, self.channels, dtype))
+                 for f in files]
+        pool.close()
+        pool.join()
+        return [t.get() for t in tasks]
+
+    # ------------------------------------------------------------------ fad.py:593-662
+    def score(self, background_dir: str, eval_dir: str, background_embds_path: Optional[str] = None,
+              eval_embds_path: Optional[str] = None, dtype: str = "float32") -> float:
+        try:
+            if background_embds_path and os.path.exists(background_embds_path):
+                if self.verbose:
+                    print(f"[Exported FAD] Loading embeddings from {background_embds_path}...")
+                embds_background = np.load(background_embds_path)
+            else:
+                audio_background = self._load_audio_files(background_dir, dtype=dtype)
+                embds_background = self.get_embeddings(audio_background, sr=self.sample_rate)
+                if background_embds_path:
+                    os.makedirs(os.path.dirname(background_embds_path), exist_ok=True)
+                    np.save(background_embds_path, embds_background)
+            if eval_embds_path and os.path.exists(eval_embds_path):
+                if self.verbose:
+                    print(f"[Exported FAD] Loading embeddings from {eval_embds_path}...")
+                embds_eval = np.load(eval_embds_path)
+            else:
+                audio_eval = self._load_audio_files(eval_dir, dtype=dtype)
+                embds_eval = self.get_embeddings(audio_eval, sr=self.sample_rate)
+                if eval_embds_path:
+                    os.makedirs(os.path.dirname(eval_embds_path), exist_ok=True)
+                    np.save(eval_embds_path, embds_eval)
+            if len(embds_background) == 0:
+                print("[Exported FAD] Background set dir is empty, exiting...")
+                return -1
+            if len(embds_eval) == 0:
+                print("[Exported FAD] Eval set dir is empty, exiting...")
+                return -1
+            mu_background, sigma_background = self.calculate_embd_statistics(embds_background)
+            mu_eval, sigma_eval = self.calculate_embd_statistics(embds_eval)
+            return self.calculate_frechet_distance(mu_background, sigma_background, mu_eval, sigma_eval)
+        except Exception as e:
+            print(f"[Exported FAD] An error occurred: {e}")
+            return -1
+
+    # ------------------------------------------------------------------ B200 extensions
+    def score_clips(self, background: torch.Tensor, evalset: torch.Tensor) -> float:
+        """FAD of two in-memory clip sets ([n, samples] fp32, host or device), sharded across the
+        ranks of `process_group` when torch.distributed is initialised: each rank embeds its shard,
+        accumulates {n, sum x, sum x x^T} in fp64, ONE all-reduce, then every rank finalises.
+        Embeddings never leave the GPU."""
+        eng = self.engine
+        accs = []
+        for clips in (background, evalset):
+            acc = eng.new_acc()
+            if clips.shape[0]:
+                emb = eng.embed_pcm(clips.to(self.device, torch.float32))
+                eng.stats_accumulate(emb, acc)
+            accs.append(acc)
+        both = torch.cat(accs)
+        eng.allreduce_acc(both, self.process_group)
+        n = both.numel() // 2
+        mu1, s1 = eng.stats_finalize(both[:n], eng.dim)
+        mu2, s2 = eng.stats_finalize(both[n:], eng.dim)
+        return float(eng.frechet(mu1, s1, mu2, s2)[0].item())
