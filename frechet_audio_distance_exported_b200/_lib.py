@@ -36,6 +36,8 @@ SYMBOLS = [
     ("fadb_stats_finalize", C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp, _vp]),
     ("fadb_frechet", C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_int, _dp, _vp]),
     ("fadb_fad_from_pcm_host", C.c_int, [_vp, _fp, _i64, _fp, _i64, _i64, _fp, _fp, C.POINTER(C.c_double)]),
+    ("fadb_profile_enable", C.c_int, [_vp, C.c_int]),
+    ("fadb_profile_read", C.c_int, [_vp, C.POINTER(C.c_double)]),
     ("fadb_launch_count", C.c_int64, [_vp]),
     ("fadb_device_status", C.c_int, [_vp]),
     ("fadb_debug_conv_layer", C.c_int,
@@ -87,9 +89,13 @@ class Handle:
         self.device = int(device)
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self.lib.fadb_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._h = None
+            try:
+                self.lib.fadb_destroy(h)
+            except Exception:          # interpreter shutdown: ctypes globals may already be gone
+                pass
 
     __del__ = close
 

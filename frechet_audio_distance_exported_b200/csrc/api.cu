@@ -423,6 +423,7 @@ void fadb_destroy(fadb_handle* h) {
     h->weight_pool.release();
     h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -646,6 +647,32 @@ int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_b
     FADB_CUDA_CHECK(cudaStreamSynchronize(st));
     *fad_out = res[0];
     return check_device_flag(h);
+}
+
+int fadb_profile_enable(fadb_handle* h, int on) {
+    if (!h) return FADB_E_INVALID;
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
+    h->prof_flops = 0.0;
+    h->profile = on != 0;
+    return FADB_OK;
+}
+
+int fadb_profile_read(fadb_handle* h, double* out4) {
+    if (!h || !out4) return FADB_E_INVALID;
+    cudaSetDevice(h->device);
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_events.size(); i += 2) {
+        FADB_CUDA_CHECK(cudaEventSynchronize(h->prof_events[i + 1]));
+        float t = 0.f;
+        FADB_CUDA_CHECK(cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]));
+        ms += t;
+    }
+    out4[0] = ms;
+    out4[1] = h->prof_flops;
+    out4[2] = (double)(h->prof_events.size() / 2);
+    out4[3] = 0.0;
+    return FADB_OK;
 }
 
 int64_t fadb_launch_count(const fadb_handle* h) { return h ? h->launches : 0; }

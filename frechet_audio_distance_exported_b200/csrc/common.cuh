@@ -118,6 +118,10 @@ struct fadb_handle {
     fadb::DevBuf ws_stats;      // fp64 workspace of fadb_fad_from_pcm_host
     fadb::DevBuf ws_pcm[2];     // double-buffered PCM chunks for the host path
     fadb::DevBuf ws_emb;        // embeddings of the host path
+    // optional per-launch timing of the tensor-core layers (bench.py roofline leg)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+    double prof_flops = 0.0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_compute[2] = {nullptr, nullptr};

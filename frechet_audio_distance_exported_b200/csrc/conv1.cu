@@ -68,33 +68,33 @@ __global__ void __launch_bounds__(256) conv1_vggish_kernel(const float* __restri
 #pragma unroll
         for (int c = 0; c < 4; ++c) in[r][c] = s_in[pr * 2 + r][pc * 2 + c];
 
-    float best[16];
+    // tap-outer loop: 16 weights are loaded once per tap and reused by the 4 positions of the pooling window
+    float acc[4][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) best[j] = -INFINITY;
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int qy = q >> 1, qx = q & 1;
-        float acc[16];
+        for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            const float4* wp = reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][g * 16]);
+            float wv[16];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float xv = in[qy + ky][qx + kx];
-                const float4* wp = reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][g * 16]);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const float4 wv = wp[v];
-                    acc[v * 4 + 0] = fmaf(xv, wv.x, acc[v * 4 + 0]);
-                    acc[v * 4 + 1] = fmaf(xv, wv.y, acc[v * 4 + 1]);
-                    acc[v * 4 + 2] = fmaf(xv, wv.z, acc[v * 4 + 2]);
-                    acc[v * 4 + 3] = fmaf(xv, wv.w, acc[v * 4 + 3]);
-                }
+            for (int v = 0; v < 4; ++v) {
+                const float4 t = wp[v];
+                wv[v * 4 + 0] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w;
             }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) best[j] = fmaxf(best[j], acc[j]);
-    }
+            for (int q = 0; q < 4; ++q) {
+                const float xv = in[(q >> 1) + ky][(q & 1) + kx];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[q][j] = fmaf(xv, wv[j], acc[q][j]);
+            }
+        }
+    float best[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) best[j] = fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j]));
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(best[j] + s_b[g * 16 + j], 0.f);   // relu(max(.)+b) == max(relu(.+b))

@@ -349,65 +349,75 @@ __global__ void tridiag_last_kernel(const double* __restrict__ A, int d, double*
 // ------------------------------------------------------------------------------------------------
 // Sturm bisection: thread i finds the i-th smallest eigenvalue of the tridiagonal (diag, off);
 // accumulates sum sqrt(max(lambda, 0)) into scal[2].
+//
+// The count "eigenvalues < x" is the number of sign changes of the leading-principal-minor sequence
+//   p_0 = 1, p_1 = a_0 - x, p_{j+1} = (a_j - x) p_j - e_{j-1}^2 p_{j-1}
+// (division-free: one dependent DFMA per step instead of an fp64 division; the e^2 p_{j-1} product is
+// off the critical path).  The matrix is scaled to spectral radius <= 1 so |p| grows by at most 2.42x
+// per step; every 8 steps the pair is renormalised by its exponent.  An exact zero takes the sign
+// opposite to its predecessor (Wilkinson's convention), which also keeps decoupled blocks (e = 0) right.
+// Fixed 56 halvings of [-1-delta, 1+delta] -> absolute accuracy ~4e-17 * radius, all that tr sqrt needs.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) bisect_kernel(const double* __restrict__ diag, const double* __restrict__ off,
                                                      int d, double* __restrict__ scal, double* __restrict__ eig_out) {
     extern __shared__ __align__(16) double bsm[];
-    double* sa = bsm;          // [d]
-    double* se2 = bsm + d;     // [d]  off^2 (se2[j] couples j and j+1)
+    double* sa = bsm;          // [d]  a / radius
+    double* se2 = bsm + d;     // [d]  (off / radius)^2 ; se2[j] couples j and j+1
     __shared__ double red[33];
-    __shared__ double s_lo, s_hi, s_piv;
-    double lo = INFINITY, hi = -INFINITY, e2max = 0.0;
+    __shared__ double s_rad;
+    double rad = 0.0;
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
-        const double a = diag[i];
         const double el = (i > 0) ? fabs(off[i - 1]) : 0.0;
         const double er = (i < d - 1) ? fabs(off[i]) : 0.0;
-        sa[i] = a;
-        se2[i] = (i < d - 1) ? off[i] * off[i] : 0.0;
-        lo = fmin(lo, a - el - er);
-        hi = fmax(hi, a + el + er);
-        e2max = fmax(e2max, er * er);
+        rad = fmax(rad, fabs(diag[i]) + el + er);                 // Gershgorin bound on the spectral radius
     }
-    lo = -warp_max(-lo); hi = warp_max(hi); e2max = warp_max(e2max);
+    rad = warp_max(rad);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rad;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = lo; }
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        s_rad = (m > 0.0 && isfinite(m)) ? m : 1.0;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { double m = INFINITY; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmin(m, red[w]); s_lo = m; }
+    const double radius = s_rad, inv = 1.0 / radius;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        sa[i] = diag[i] * inv;
+        const double e = (i < d - 1) ? off[i] * inv : 0.0;
+        se2[i] = e * e;
+    }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = hi; }
-    __syncthreads();
-    if (threadIdx.x == 0) { double m = -INFINITY; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]); s_hi = m; }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = e2max; }
-    __syncthreads();
-    if (threadIdx.x == 0) { double m = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]); s_piv = 2.2250738585072014e-308 * fmax(1.0, m) * 1e4; }
-    __syncthreads();
-    const double pivmin = s_piv;
-    const double nrm = fmax(fabs(s_lo), fabs(s_hi));
-    const double gl = s_lo - (2.0 * nrm * 2.220446049250313e-16 * d + 2.0 * pivmin);
-    const double gu = s_hi + (2.0 * nrm * 2.220446049250313e-16 * d + 2.0 * pivmin);
 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     double contrib = 0.0;
     if (idx < d) {
-        double a = gl, b = gu;
-        for (int it = 0; it < 128; ++it) {
-            const double mid = 0.5 * (a + b);
-            if (!(mid > a) || !(mid < b)) break;
-            // number of eigenvalues < mid
-            int cnt = 0;
-            double q = sa[0] - mid;
-            if (fabs(q) < pivmin) q = -pivmin;
-            cnt += (q < 0.0);
-            for (int j = 1; j < d; ++j) {
-                q = sa[j] - mid - se2[j - 1] / q;
-                if (fabs(q) < pivmin) q = -pivmin;
-                cnt += (q < 0.0);
+        double lo = -1.0 - 1e-9, hi = 1.0 + 1e-9;
+        for (int it = 0; it < 56; ++it) {
+            const double x = 0.5 * (lo + hi);
+            double pp = 1.0;
+            double pc = sa[0] - x;
+            if (pc == 0.0) pc = -1e-30;
+            int cnt = (pc < 0.0);
+            for (int j0 = 1; j0 < d; j0 += 8) {
+                const int j1 = (j0 + 8 < d) ? j0 + 8 : d;
+                for (int j = j0; j < j1; ++j) {
+                    double pn = fma(sa[j] - x, pc, -(se2[j - 1] * pp));
+                    if (pn == 0.0) pn = -pc * 7.888609052210118e-31;          // 2^-100, opposite sign
+                    cnt += (__double2hiint(pn) ^ __double2hiint(pc)) < 0;     // sign change
+                    pp = pc;
+                    pc = pn;
+                }
+                // renormalise the pair by the exponent of |pc| (keeps everything far from over/underflow)
+                const int ex = ((__double2hiint(pc) >> 20) & 0x7ff) - 1023;
+                if (ex > 200 || ex < -200) {
+                    const double sc = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
+                    pc *= sc;
+                    pp *= sc;
+                }
             }
-            if (cnt > idx) b = mid; else a = mid;
-            if (b - a <= 2.0 * 2.220446049250313e-16 * fmax(fabs(a), fabs(b)) + 2.0 * pivmin) break;
+            if (cnt > idx) hi = x; else lo = x;
         }
-        const double lam = 0.5 * (a + b);
+        const double lam = 0.5 * (lo + hi) * radius;
         if (eig_out) eig_out[idx] = lam;
         contrib = sqrt(fmax(lam, 0.0));
     }

@@ -9,10 +9,12 @@
 //            fad.py:41-66 (zero rows up to T' = 32k-24)
 //   CLAP   : models/clap.py:70-72 (int16 truncation), fad.py:356-359 (zero-pad to 480000), fad.py:69-91
 //
-// Arithmetic: the FFT runs in fp64 like the reference (numpy promotes float32 PCM x float64 window
-// to float64; librosa evaluates the FFT in float64) — an fp32 FFT leaves a noise floor that breaks
-// 1e-5 log-mel parity on tonal inputs (empty bins sit at log(0.01)).  Real FFT of length NF as a
-// complex Stockham FFT of length NF/2 (radix-4 passes + one radix-2 pass when needed) + split.
+// Arithmetic: windowing, FFT and the real-FFT split run in fp64 like the reference (numpy promotes
+// float32 PCM x float64 window to float64; librosa evaluates the FFT in float64) — an fp32 FFT leaves a
+// noise floor that breaks 1e-5 log-mel parity on tonal inputs (empty bins sit at log(0.01)).  From the
+// spectrum on (|X|, mel projection, log) fp32 is enough: sums of positives, relative error ~1e-7.
+// Real FFT of length NF = complex in-place Stockham FFT of length NF/2 (radix-4 passes + one radix-2
+// pass when needed, inputs of a pass staged in registers) + split.
 #include <cmath>
 #include <vector>
 
@@ -26,7 +28,7 @@ struct FrontTables {
     int* band_start = nullptr; // [64]
     int* band_len = nullptr;   // [64]
     int* band_off = nullptr;   // [64]
-    double* band_w = nullptr;  // [sum len]
+    float* band_w = nullptr;   // [sum len] fp32
     int nfft = 0, win_len = 0, hop = 0;
     bool ready = false;
 };
@@ -46,149 +48,191 @@ struct FrontParams {
     const int* band_start;
     const int* band_len;
     const int* band_off;
-    const double* band_w;
+    const float* band_wf;
     float* out;         // [n_clips][rows_out][64]
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// One in-place Stockham pass of radix R over the warp's M-point buffer: every lane first pulls ALL of
+// its butterfly inputs into registers, the warp syncs, then the outputs go back to the same buffer.
+template <int M, int R, bool FIRST>
+__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ tw, int pp, int tstep,
+                                         int lane) {
+    constexpr int T = M / R;                 // butterflies in the pass
+    constexpr int PER = (T + 31) / 32;       // per lane
+    double2 u[PER][R];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = lane + 32 * q;
+        if (T >= 32 || i < T) {
+            const int k = i & (pp - 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double2 v = x[i + r * T];
+                if (!FIRST && r > 0) v = cmul(v, tw[r * k * tstep]);
+                u[q][r] = v;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = lane + 32 * q;
+        if (T >= 32 || i < T) {
+            const int k = i & (pp - 1);
+            const int j = (i - k) * R + k;
+            if (R == 4) {
+                const double2 v0 = cadd(u[q][0], u[q][2]);
+                const double2 v1 = csub(u[q][0], u[q][2]);
+                const double2 v2 = cadd(u[q][1], u[q][3]);
+                const double2 d = csub(u[q][1], u[q][3]);
+                const double2 v3 = make_double2(d.y, -d.x);          // -i * d
+                x[j] = cadd(v0, v2);
+                x[j + pp] = cadd(v1, v3);
+                x[j + 2 * pp] = csub(v0, v2);
+                x[j + 3 * pp] = csub(v1, v3);
+            } else {
+                x[j] = cadd(u[q][0], u[q][1]);
+                x[j + pp] = csub(u[q][0], u[q][1]);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// complex FFT of length M (power of two, 128/256/512) as radix-4 passes (+ one radix-2 pass for odd log2)
+template <int M, int NF>
+__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ tw, int lane) {
+    if (M == 256) {
+        fft_pass<M, 4, true>(x, tw, 1, NF / 4, lane);
+        fft_pass<M, 4, false>(x, tw, 4, NF / 16, lane);
+        fft_pass<M, 4, false>(x, tw, 16, NF / 64, lane);
+        fft_pass<M, 4, false>(x, tw, 64, NF / 256, lane);
+    } else if (M == 128) {
+        fft_pass<M, 4, true>(x, tw, 1, NF / 4, lane);
+        fft_pass<M, 4, false>(x, tw, 4, NF / 16, lane);
+        fft_pass<M, 4, false>(x, tw, 16, NF / 64, lane);
+        fft_pass<M, 2, false>(x, tw, 64, NF / 128, lane);
+    } else {
+        fft_pass<M, 4, true>(x, tw, 1, NF / 4, lane);
+        fft_pass<M, 4, false>(x, tw, 4, NF / 16, lane);
+        fft_pass<M, 4, false>(x, tw, 16, NF / 64, lane);
+        fft_pass<M, 4, false>(x, tw, 64, NF / 256, lane);
+        fft_pass<M, 2, false>(x, tw, 256, NF / 512, lane);
+    }
+}
+
+constexpr int kFrontWarps = 8;
+constexpr int kFramesPerWarp = 8;
 
 template <int NF>
-__global__ void __launch_bounds__(256) fadb_frontend_kernel(const FrontParams p) {
+__global__ void __launch_bounds__(kFrontWarps * 32) fadb_frontend_kernel(const FrontParams p) {
     constexpr int M = NF / 2;
+    constexpr int SPEC_PITCH = M + 4;        // floats per warp spectrum (M + 1 used)
     extern __shared__ __align__(16) uint8_t fsm[];
-    double2* s_tw = reinterpret_cast<double2*>(fsm);                       // [NF]
-    double* s_win = reinterpret_cast<double*>(fsm + NF * 16);              // [NF] (zero beyond win_len)
-    double2* s_buf = reinterpret_cast<double2*>(fsm + NF * 16 + NF * 8);   // [8 warps][2][M]
+    double2* s_tw = reinterpret_cast<double2*>(fsm);                                  // [NF]
+    double* s_win = reinterpret_cast<double*>(fsm + NF * 16);                         // [NF] (zero beyond win_len)
+    double2* s_buf = reinterpret_cast<double2*>(fsm + NF * 16 + NF * 8);              // [warps][M]
+    float* s_spec = reinterpret_cast<float*>(fsm + NF * 16 + NF * 8 + kFrontWarps * M * 16);   // [warps][SPEC_PITCH]
 
-    for (int i = threadIdx.x; i < NF; i += 256) {
+    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) {
         s_tw[i] = p.tw[i];
         s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2* bufA = s_buf + warp * 2 * M;
-    double2* bufB = bufA + M;
+    double2* x = s_buf + warp * M;
+    float* spec = s_spec + warp * SPEC_PITCH;
     const int clip = blockIdx.y;
     const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
     float* out = p.out + (size_t)clip * p.rows_out * 64;
+    // this lane's two mel bands
+    int bst[2], bln[2], bof[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        bst[h2] = p.band_start[lane + 32 * h2];
+        bln[h2] = p.band_len[lane + 32 * h2];
+        bof[h2] = p.band_off[lane + 32 * h2];
+    }
 
-    for (int fi = 0; fi < 8; ++fi) {
-        const int row = blockIdx.x * 64 + warp * 8 + fi;
+    for (int fi = 0; fi < kFramesPerWarp; ++fi) {
+        const int row = blockIdx.x * (kFrontWarps * kFramesPerWarp) + warp * kFramesPerWarp + fi;
         if (row >= p.rows_out) break;
         if (row >= p.frames_valid) {                 // PANN time padding: literal zero rows (fad.py:61-64)
             out[(size_t)row * 64 + lane] = 0.f;
             out[(size_t)row * 64 + lane + 32] = 0.f;
             continue;
         }
-        // ---- load + window: z[n] = x[2n] + i x[2n+1]
+        // ---- load + window (fp32 PCM x fp64 Hann, like numpy's promotion): z[n] = x[2n] + i x[2n+1]
         const long long f0 = (long long)row * p.hop - (p.centered ? NF / 2 : 0);
-        for (int n = lane; n < M; n += 32) {
-            double v[2];
+        const bool interior = (f0 >= 0) && (f0 + p.win_len <= p.n_samples);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = 2 * n + e;
-                float s = 0.f;
-                if (j < p.win_len) {
-                    long long src = f0 + j;
-                    if (p.centered) {                // np.pad(mode='reflect'): edge sample not repeated
-                        if (src < 0) src = -src;
-                        if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
-                    }
-                    if (src >= 0 && src < p.n_samples) s = __ldg(pcm + src);
-                    if (p.quantize) {                // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
-                        const float q = truncf(__fmul_rn(s, 32767.0f));
-                        s = __fdiv_rn(q, 32767.0f);
+        for (int q = 0; q < M / 32; ++q) {
+            const int n = lane + 32 * q;
+            float s0 = 0.f, s1 = 0.f;
+            if (2 * n < p.win_len) {
+                if (interior) {
+                    s0 = __ldg(pcm + f0 + 2 * n);
+                    s1 = (2 * n + 1 < p.win_len) ? __ldg(pcm + f0 + 2 * n + 1) : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 2 * n + e;
+                        float s = 0.f;
+                        if (j < p.win_len) {
+                            long long src = f0 + j;
+                            if (p.centered) {        // np.pad(mode='reflect'): edge sample not repeated
+                                if (src < 0) src = -src;
+                                if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
+                            }
+                            if (src >= 0 && src < p.n_samples) s = __ldg(pcm + src);
+                        }
+                        if (e == 0) s0 = s; else s1 = s;
                     }
                 }
-                v[e] = (double)s * s_win[j];
+                if (p.quantize) {                    // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
+                    s0 = __fdiv_rn(truncf(__fmul_rn(s0, 32767.0f)), 32767.0f);
+                    s1 = __fdiv_rn(truncf(__fmul_rn(s1, 32767.0f)), 32767.0f);
+                }
             }
-            bufA[n] = make_double2(v[0], v[1]);
+            x[n] = make_double2((double)s0 * s_win[2 * n], (double)s1 * s_win[2 * n + 1]);
         }
         __syncwarp();
 
-        // ---- complex Stockham FFT of length M (forward)
-        double2* x = bufA;
-        double2* y = bufB;
-        int pp = 1;
-        while (pp < M) {
-            const bool r4 = ((M / pp) % 4) == 0;
-            if (r4) {
-                const int T = M / 4;
-                const int tstep = NF / (pp * 4);
-                for (int i = lane; i < T; i += 32) {
-                    const int k = i & (pp - 1);
-                    double2 u0 = x[i];
-                    double2 u1 = cmul(x[i + T], s_tw[k * tstep]);
-                    double2 u2 = cmul(x[i + 2 * T], s_tw[2 * k * tstep]);
-                    double2 u3 = cmul(x[i + 3 * T], s_tw[3 * k * tstep]);
-                    const double2 v0 = make_double2(u0.x + u2.x, u0.y + u2.y);
-                    const double2 v1 = make_double2(u0.x - u2.x, u0.y - u2.y);
-                    const double2 v2 = make_double2(u1.x + u3.x, u1.y + u3.y);
-                    const double2 d = make_double2(u1.x - u3.x, u1.y - u3.y);
-                    const double2 v3 = make_double2(d.y, -d.x);          // -i * d
-                    const int j = (i - k) * 4 + k;
-                    y[j] = make_double2(v0.x + v2.x, v0.y + v2.y);
-                    y[j + pp] = make_double2(v1.x + v3.x, v1.y + v3.y);
-                    y[j + 2 * pp] = make_double2(v0.x - v2.x, v0.y - v2.y);
-                    y[j + 3 * pp] = make_double2(v1.x - v3.x, v1.y - v3.y);
-                }
-                pp *= 4;
-            } else {
-                const int T = M / 2;
-                const int tstep = NF / (pp * 2);
-                for (int i = lane; i < T; i += 32) {
-                    const int k = i & (pp - 1);
-                    const double2 u0 = x[i];
-                    const double2 u1 = cmul(x[i + T], s_tw[k * tstep]);
-                    const int j = (i - k) * 2 + k;
-                    y[j] = make_double2(u0.x + u1.x, u0.y + u1.y);
-                    y[j + pp] = make_double2(u0.x - u1.x, u0.y - u1.y);
-                }
-                pp *= 2;
+        fft_inplace<M, NF>(x, s_tw, lane);
+
+        // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32
+#pragma unroll
+        for (int q = 0; q <= M / 32; ++q) {
+            const int k = lane + 32 * q;
+            if (k <= M) {
+                const double2 a = x[k & (M - 1)];
+                const double2 bz = x[(M - k) & (M - 1)];
+                const double2 ze = make_double2(0.5 * (a.x + bz.x), 0.5 * (a.y - bz.y));
+                const double2 zo = make_double2(0.5 * (a.y + bz.y), -0.5 * (a.x - bz.x));   // (a - conj b) / (2i)
+                const double2 w = s_tw[k];                                                   // tw[M] = -1
+                const float re = (float)(ze.x + w.x * zo.x - w.y * zo.y);
+                const float im = (float)(ze.y + w.x * zo.y + w.y * zo.x);
+                const float pw = fmaf(re, re, im * im);
+                spec[k] = p.power_db ? pw : sqrtf(pw);
             }
-            __syncwarp();
-            double2* t = x; x = y; y = t;
-        }
-        // x holds Z[0..M); y is free -> spectrum as doubles spec[0..M]
-        double* spec = reinterpret_cast<double*>(y);
-        for (int k = lane; k <= M; k += 32) {
-            const double2 a = x[k & (M - 1)];
-            const double2 bz = x[(M - k) & (M - 1)];
-            const double2 b = make_double2(bz.x, -bz.y);                 // conj
-            const double2 ze = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
-            const double2 dd = make_double2(a.x - b.x, a.y - b.y);       // (a-b)/(2i) = (dd.y - i dd.x)/2
-            const double2 zo = make_double2(0.5 * dd.y, -0.5 * dd.x);
-            const double2 w = s_tw[k];                                   // tw[M] = -1
-            const double2 X = make_double2(ze.x + w.x * zo.x - w.y * zo.y, ze.y + w.x * zo.y + w.y * zo.x);
-            double sv;
-            if (p.power_db) {                                            // complex64 -> |.| float32 -> ^2 (pann.py:118)
-                const float re = (float)X.x, im = (float)X.y;
-                const float mag = hypotf(re, im);
-                sv = (double)__fmul_rn(mag, mag);
-            } else {
-                sv = sqrt(X.x * X.x + X.y * X.y);                        // vggish.py:141
-            }
-            spec[k] = sv;
         }
         __syncwarp();
-        // ---- mel projection (sparse triangular bands) + log
+        // ---- mel projection (sparse triangular bands) + log, fp32
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const int b = lane + 32 * h2;
-            const int st = p.band_start[b], ln = p.band_len[b], off = p.band_off[b];
-            double acc = 0.0;
-            for (int i = 0; i < ln; ++i) acc = fma(__ldg(p.band_w + off + i), spec[st + i], acc);
+            float acc = 0.f;
+            for (int i = 0; i < bln[h2]; ++i) acc = fmaf(__ldg(p.band_wf + bof[h2] + i), spec[bst[h2] + i], acc);
             float o;
-            if (p.power_db) {
-                const float m32 = fmaxf((float)acc, 1e-10f);
-                o = (float)(10.0 * log10((double)m32));                  // pann.py:133-134
-            } else {
-                o = (float)log(acc + 0.01);                              // vggish.py:227
-            }
-            out[(size_t)row * 64 + b] = o;
+            if (p.power_db) o = 10.0f * log10f(fmaxf(acc, 1e-10f));      // pann.py:133-134
+            else o = logf(acc + 0.01f);                                  // vggish.py:227
+            out[(size_t)row * 64 + lane + 32 * h2] = o;
         }
         __syncwarp();
     }
@@ -266,34 +310,36 @@ static int build_tables(int model) {
     if (model == FADB_MODEL_VGGISH) vggish_mel(t.nfft / 2 + 1, wc);
     else slaney_mel(sr, t.nfft, fmin, fmax, wc);
     std::vector<int> bs(64), bl(64), bo(64);
-    std::vector<double> bw;
+    std::vector<float> bw;
     for (int b = 0; b < 64; ++b) {
         int first = -1, last = -1;
         for (int k = 0; k < (int)wc[b].size(); ++k)
             if (wc[b][k] != 0.0) { if (first < 0) first = k; last = k; }
         if (first < 0) { first = 0; last = -1; }
         bs[b] = first; bl[b] = last - first + 1; bo[b] = (int)bw.size();
-        for (int k = first; k <= last; ++k) bw.push_back(wc[b][k]);
+        for (int k = first; k <= last; ++k) bw.push_back((float)wc[b][k]);
     }
-    if (bw.empty()) bw.push_back(0.0);
+    if (bw.empty()) bw.push_back(0.f);
     FADB_CUDA_CHECK(cudaMalloc(&t.tw, tw.size() * sizeof(double2)));
     FADB_CUDA_CHECK(cudaMalloc(&t.win, win.size() * sizeof(double)));
     FADB_CUDA_CHECK(cudaMalloc(&t.band_start, 64 * sizeof(int)));
     FADB_CUDA_CHECK(cudaMalloc(&t.band_len, 64 * sizeof(int)));
     FADB_CUDA_CHECK(cudaMalloc(&t.band_off, 64 * sizeof(int)));
-    FADB_CUDA_CHECK(cudaMalloc(&t.band_w, bw.size() * sizeof(double)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.band_w, bw.size() * sizeof(float)));
     FADB_CUDA_CHECK(cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.win, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.band_start, bs.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.band_len, bl.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.band_off, bo.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
-    FADB_CUDA_CHECK(cudaMemcpy(t.band_w, bw.data(), bw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.band_w, bw.data(), bw.size() * sizeof(float), cudaMemcpyHostToDevice));
     t.ready = true;
     return FADB_OK;
 }
 
 template <int NF>
-static constexpr int front_smem() { return NF * 16 + NF * 8 + 8 * 2 * (NF / 2) * 16; }
+static constexpr int front_smem() {
+    return NF * 16 + NF * 8 + kFrontWarps * (NF / 2) * 16 + kFrontWarps * (NF / 2 + 4) * 4;
+}
 
 int frontend_init(fadb_handle* h) {
     (void)h;
@@ -347,7 +393,7 @@ int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips
     p.power_db = (model != FADB_MODEL_VGGISH);
     p.quantize = (model == FADB_MODEL_CLAP);
     p.tw = t.tw; p.win = t.win;
-    p.band_start = t.band_start; p.band_len = t.band_len; p.band_off = t.band_off; p.band_w = t.band_w;
+    p.band_start = t.band_start; p.band_len = t.band_len; p.band_off = t.band_off; p.band_wf = t.band_w;
     p.out = feats;
     if (model == FADB_MODEL_VGGISH) {
         const int64_t patches = frontend_rows(model, n_samples);

@@ -16,8 +16,9 @@
 //     MMAs of tile i+1.
 //   * split-bf16 ("bf16x3") mode: the K loop runs three passes (A_hi*B_hi, A_lo*B_hi, A_hi*B_lo)
 //     into the same accumulator, giving ~2^-16 relative operand precision with the same kernel.
-//   * Epilogue (4 warps): tcgen05.ld -> +bias (folded BN) -> ReLU -> fp32 staging tile in smem ->
-//     optional 2x2 max / avg pool -> bf16 hi(/lo) or fp32 NHWC, 16-byte stores.
+//   * Epilogue (4 warps): tcgen05.ld -> +bias (folded BN) -> ReLU -> optional 2x2 max / avg pool done with
+//     two warp shuffles per value (the pooled layers use boxes <= 16 pixels wide, so a pooling window
+//     lives inside one warp) -> bf16 hi(/lo) or fp32 NHWC, 16-byte stores straight from registers.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
@@ -56,17 +57,14 @@ constexpr int kThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // one 128-byte swizzle atom of bf16
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16384
-constexpr int kStagePitch = 33;                   // fp32 staging row pitch (bank-conflict free)
-constexpr int kStagingBytes = kTileM * kStagePitch * 4;
 
 template <int BN>
 struct GemmCfg {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int kTmemCols = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + BN * 4 /*bias*/ + 256 /*barriers*/ +
-                                      1024 /*alignment slack*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -173,7 +171,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 //   start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B (8 rows x 128 B) | layout type 2
@@ -205,9 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     const uint32_t base = (raw_addr + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-B alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    float* staging = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
-    float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + kStagingBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + kStagingBytes + BN * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages]
     const uint32_t bar_tfull = bar_empty + 8 * kStages;              // [2]
@@ -310,9 +305,17 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         }
     } else if (warp >= 4) {
         // ======================= epilogue =======================
+        // Thread = one accumulator row (pixel); a chunk = 32 output channels held in registers.
+        // 2x2 pooling never leaves the warp: the tile box is at most 16 pixels wide, so a warp holds an
+        // even number of complete tile rows and the 4 pixels of a pooling window are lanes
+        // {l, l^1, l^BW, l^BW^1} -> two shuffles per value, no shared-memory staging, no block barrier.
         const int ew = warp - 4;                     // TMEM lane quarter
-        const int et = threadIdx.x - 128;            // 0..127
         const int row = ew * 32 + lane;              // accumulator row (= pixel within the tile)
+        const int ww = row % p.BW;
+        const int t2 = row / p.BW;
+        const int hh = t2 % p.BH;
+        const int bb = t2 / p.BH;
+        const bool pool_lane = ((lane & 1) == 0) && ((lane & p.BW) == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -322,9 +325,17 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             const int wt = m % p.tiles_w; m /= p.tiles_w;
             const int ht = m % p.tiles_h;
             const int bt = m / p.tiles_h;
-            const int x0 = wt * p.BW, y0 = ht * p.BH, b0 = bt * p.BB;
-
-            for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+            const int x = wt * p.BW + ww, y = ht * p.BH + hh, b = bt * p.BB + bb;
+            bool valid;
+            size_t obase;
+            if (p.pool) {
+                const int px = x >> 1, py = y >> 1;
+                valid = pool_lane && px < p.Wo && py < p.Ho && b < p.B;
+                obase = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + n0;
+            } else {
+                valid = x < p.W && y < p.H && b < p.B;
+                obase = ((size_t(b) * p.Ho + y) * p.Wo + x) * p.N + n0;
+            }
 
             mbar_wait(bar_tfull + 8 * as, aphase, p.err_flag);
             tc_fence_after();
@@ -341,96 +352,69 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
                 }
-                epi_bar_sync();                      // previous chunk fully consumed (and bias_s visible)
+                float v[32];
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v = __uint_as_float(r[j]) + bias_s[c * 32 + j];
-                    if (p.relu) v = fmaxf(v, 0.f);
-                    staging[row * kStagePitch + j] = v;
-                }
-                epi_bar_sync();                      // staging tile complete
-
-                const int nb = n0 + c * 32;
-                if (p.pool == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int item = et + 128 * i;
-                        const int rr = item >> 2, g = item & 3;
-                        const int ww = rr % p.BW;
-                        const int t2 = rr / p.BW;
-                        const int hh = t2 % p.BH;
-                        const int bb = t2 / p.BH;
-                        const int x = x0 + ww, y = y0 + hh, b = b0 + bb;
-                        if (x < p.W && y < p.H && b < p.B) {
-                            const float* s = staging + rr * kStagePitch + g * 8;
-                            const size_t o = ((size_t(b) * p.Ho + y) * p.Wo + x) * p.N + nb + g * 8;
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = s[j];
-                            if (p.out_f32) {
-                                float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
-                                d[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                d[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            } else {
-                                uint4 hi;
-                                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                                *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
-                                if (p.out_lo) {
-                                    uint4 lo;
-                                    lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-                                    lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-                                    lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-                                    lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-                                    *reinterpret_cast<uint4*>(p.out_lo + o) = lo;
-                                }
-                            }
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bv = __ldg(bp + q);
+                        v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bv.x;
+                        v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bv.y;
+                        v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bv.z;
+                        v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bv.w;
                     }
                 } else {
-                    // 2x2 pooling inside the tile: 32 pooled pixels x 4 channel groups = 128 items
-                    const int pp = et >> 2, g = et & 3;
-                    const int hw = p.BW >> 1, hh2 = p.BH >> 1;
-                    const int pw = pp % hw;
-                    const int t2 = pp / hw;
-                    const int ph = t2 % hh2;
-                    const int pb = t2 / hh2;
-                    const int px = (x0 >> 1) + pw, py = (y0 >> 1) + ph, b = b0 + pb;
-                    if (px < p.Wo && py < p.Ho && b < p.B) {
-                        const int r00 = (pb * p.BH + 2 * ph) * p.BW + 2 * pw;
-                        const float* s0 = staging + r00 * kStagePitch + g * 8;
-                        const float* s1 = s0 + kStagePitch;
-                        const float* s2 = s0 + p.BW * kStagePitch;
-                        const float* s3 = s2 + kStagePitch;
-                        float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (p.pool == 1) v[j] = fmaxf(fmaxf(s0[j], s1[j]), fmaxf(s2[j], s3[j]));
-                            else v[j] = ((s0[j] + s1[j]) + (s2[j] + s3[j])) * 0.25f;
-                        }
-                        const size_t o = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + nb + g * 8;
-                        if (p.out_f32) {
-                            float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
-                            d[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            d[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.pool == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], p.BW));
+                    }
+                } else if (p.pool == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+                        v[j] += __shfl_xor_sync(0xffffffffu, v[j], p.BW);
+                        v[j] *= 0.25f;
+                    }
+                }
+                if (valid) {
+                    const size_t o = obase + c * 32;
+                    if (p.out_f32) {
+                        float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+                        uint4* d = reinterpret_cast<uint4*>(p.out_hi + o);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
                             uint4 hi;
-                            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                            *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
-                            if (p.out_lo) {
+                            hi.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]); hi.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                            hi.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); hi.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+                            d[q] = hi;
+                        }
+                        if (p.out_lo) {
+                            uint4* e = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
                                 uint4 lo;
-                                lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-                                lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-                                lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-                                lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-                                *reinterpret_cast<uint4*>(p.out_lo + o) = lo;
+                                lo.x = pack_bf16x2(v[8 * q + 0] - bf16_round(v[8 * q + 0]), v[8 * q + 1] - bf16_round(v[8 * q + 1]));
+                                lo.y = pack_bf16x2(v[8 * q + 2] - bf16_round(v[8 * q + 2]), v[8 * q + 3] - bf16_round(v[8 * q + 3]));
+                                lo.z = pack_bf16x2(v[8 * q + 4] - bf16_round(v[8 * q + 4]), v[8 * q + 5] - bf16_round(v[8 * q + 5]));
+                                lo.w = pack_bf16x2(v[8 * q + 6] - bf16_round(v[8 * q + 6]), v[8 * q + 7] - bf16_round(v[8 * q + 7]));
+                                e[q] = lo;
                             }
                         }
                     }
                 }
             }
-            epi_bar_sync();   // bias_s / staging free before the next tile overwrites them
         }
     }
 
@@ -521,6 +505,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         BW = 1;
         while (BW * 2 <= io.W && BW * 2 <= kTileM) BW *= 2;        // largest power of two <= W
         FADB_REQUIRE(BW == io.W, "W=%d must be a power of two below 128 or >= 128", io.W);
+        if (io.pool && BW > 16) BW = 16;                           // pooling window must live inside one warp
         BH = kTileM / BW;
         if (BH > io.H) {
             // fewer rows than the box: pick the power-of-two row count that wastes the fewest box rows
@@ -540,7 +525,9 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         }
     }
     FADB_REQUIRE(BW * BH * BB == kTileM, "cannot tile W=%d H=%d into 128-pixel boxes", io.W, io.H);
-    if (io.pool) FADB_REQUIRE(BW % 2 == 0 && BH % 2 == 0, "pooling needs even box dims (BW=%d BH=%d)", BW, BH);
+    if (io.pool)
+        FADB_REQUIRE(BW % 2 == 0 && BH % 2 == 0 && BW <= 16 && io.W % 2 == 0,
+                     "pooling needs an even box at most 16 wide (BW=%d BH=%d W=%d)", BW, BH, io.W);
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -578,10 +565,22 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     FADB_REQUIRE(p.out_f32 || p.out_hi, "layer has no output buffer");
 
     const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->profile) {
+        FADB_CUDA_CHECK(cudaEventCreate(&ev0));
+        FADB_CUDA_CHECK(cudaEventCreate(&ev1));
+        FADB_CUDA_CHECK(cudaEventRecord(ev0, st));
+    }
     if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, GemmCfg<256>::kSmemBytes, st>>>(p);
     else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, GemmCfg<128>::kSmemBytes, st>>>(p);
     else fadb_gemm_tc_kernel<64><<<grid, kThreads, GemmCfg<64>::kSmemBytes, st>>>(p);
     h->launches++;
+    if (h->profile) {
+        FADB_CUDA_CHECK(cudaEventRecord(ev1, st));
+        h->prof_events.push_back(ev0);
+        h->prof_events.push_back(ev1);
+        h->prof_flops += 2.0 * double(io.B) * io.H * io.W * double(L.N) * double(L.K);   // algorithmic (1 pass)
+    }
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
 }

@@ -134,9 +134,8 @@ class Engine:
 
     def allreduce_acc(self, acc: torch.Tensor, group=None) -> None:
         """The only collective of the path: one NCCL all-reduce (sum, fp64) of {n, sum x, sum x x^T}."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        from .dist import allreduce_acc
+        allreduce_acc(acc, group)
 
     # ------------------------------------------------------------------ Frechet
     def frechet(self, mu1, sigma1, mu2, sigma2) -> torch.Tensor:
@@ -168,6 +167,15 @@ class Engine:
         if return_embeddings:
             return out.value, eb.numpy(), ee.numpy()
         return out.value
+
+    def profile_enable(self, on: bool = True) -> None:
+        check(self.lib.fadb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """-> (tensor-core layer ms, algorithmic FLOPs, launches) since profile_enable(True)."""
+        out = (C.c_double * 4)()
+        check(self.lib.fadb_profile_read(self.h, out))
+        return float(out[0]), float(out[1]), int(out[2])
 
     def launch_count(self) -> int:
         return self.handle.launch_count()

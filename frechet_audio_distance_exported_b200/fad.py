@@ -329,22 +329,52 @@ class FrechetAudioDistance:
             return -1
 
     # ------------------------------------------------------------------ B200 extensions
-    def score_clips(self, background: torch.Tensor, evalset: torch.Tensor) -> float:
-        """FAD of two in-memory clip sets ([n, samples] fp32, host or device), sharded across the
-        ranks of `process_group` when torch.distributed is initialised: each rank embeds its shard,
-        accumulates {n, sum x, sum x x^T} in fp64, ONE all-reduce, then every rank finalises.
-        Embeddings never leave the GPU."""
+    def accumulate_clips(self, clips: torch.Tensor, acc: torch.Tensor, chunk_clips: int = 1024) -> None:
+        """Embed `clips` ([n, samples] fp32, HOST or device) and add their rows to the fp64 statistics
+        buffer `acc`.  Host tensors are streamed in chunks through two device buffers on a copy
+        stream so the host->device copy of chunk i+1 overlaps the kernels of chunk i (pin the host
+        tensor for this to be asynchronous).  Embeddings never leave the GPU."""
         eng = self.engine
-        accs = []
-        for clips in (background, evalset):
-            acc = eng.new_acc()
-            if clips.shape[0]:
-                emb = eng.embed_pcm(clips.to(self.device, torch.float32))
-                eng.stats_accumulate(emb, acc)
-            accs.append(acc)
-        both = torch.cat(accs)
+        n = clips.shape[0]
+        if n == 0:
+            return
+        if clips.is_cuda:
+            eng.stats_accumulate(eng.embed_pcm(clips.to(torch.float32)), acc)
+            return
+        assert clips.dtype == torch.float32 and clips.dim() == 2 and clips.is_contiguous()
+        chunk = min(chunk_clips, n)
+        if getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1]):
+            self._h2d_bufs = [torch.empty((chunk, clips.shape[1]), dtype=torch.float32, device=self.device)
+                              for _ in range(2)]
+            self._h2d_stream = torch.cuda.Stream()
+            self._h2d_copied = [torch.cuda.Event(), torch.cuda.Event()]
+            self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        cur = torch.cuda.current_stream()
+        self._h2d_stream.wait_stream(cur)
+        for i, c0 in enumerate(range(0, n, chunk)):
+            b = i & 1
+            nc = min(chunk, n - c0)
+            with torch.cuda.stream(self._h2d_stream):
+                if i >= 2:
+                    self._h2d_stream.wait_event(self._h2d_done[b])
+                self._h2d_bufs[b][:nc].copy_(clips[c0:c0 + nc], non_blocking=True)
+                self._h2d_copied[b].record(self._h2d_stream)
+            cur.wait_event(self._h2d_copied[b])
+            eng.stats_accumulate(eng.embed_pcm(self._h2d_bufs[b][:nc]), acc)
+            self._h2d_done[b].record(cur)
+
+    def score_clips(self, background: torch.Tensor, evalset: torch.Tensor) -> float:
+        """FAD of two in-memory clip sets ([n, samples] fp32, host or device).  With torch.distributed
+        initialised each rank passes ITS shard (see dist.shard_bounds): it embeds the shard,
+        accumulates {n, sum x, sum x x^T} in fp64, ONE all-reduce over `process_group`, then every
+        rank finalises mean/covariance and the Frechet distance redundantly."""
+        eng = self.engine
+        d = eng.dim
+        both = torch.zeros(2 * (1 + d + d * d), dtype=torch.float64, device=self.device)
+        half = both.numel() // 2
+        self.accumulate_clips(background, both[:half])
+        self.accumulate_clips(evalset, both[half:])
         eng.allreduce_acc(both, self.process_group)
-        n = both.numel() // 2
-        mu1, s1 = eng.stats_finalize(both[:n], eng.dim)
-        mu2, s2 = eng.stats_finalize(both[n:], eng.dim)
+        mu1, s1 = eng.stats_finalize(both[:half], d)
+        mu2, s2 = eng.stats_finalize(both[half:], d)
         return float(eng.frechet(mu1, s1, mu2, s2)[0].item())

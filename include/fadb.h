@@ -137,6 +137,11 @@ int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_b
                            double* fad_out);
 
 /* ---------------------------------------------------------------- introspection / tests */
+/* Per-launch CUDA-event timing of the tensor-core layers (for the roofline figure in bench.py):
+ * enable(1) resets the counters; read() synchronises the recorded events and returns
+ * out4 = { sum of layer launch durations in ms, algorithmic FLOPs of those launches, launches, 0 }. */
+int fadb_profile_enable(fadb_handle* h, int on);
+int fadb_profile_read(fadb_handle* h, double* out4);
 /* number of kernels this library has launched on this handle since creation */
 int64_t fadb_launch_count(const fadb_handle* h);
 /* device-side error flag (0 = none); non-zero after a pipeline timeout */

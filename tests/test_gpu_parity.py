@@ -1,0 +1,296 @@
+"""GPU parity tests (run with -m gpu on a B200): every kernel family of libfadb200.so, called
+through the C ABI (ctypes, via Engine / the façade), against the CPU oracle and against the golden
+vectors the UNMODIFIED reference produced (tests/golden/, oracle/make_golden.py).
+
+Tolerances (BASELINE.json north_star): log-mel 1e-5 relative (norm-wise: max|a-b| / max|b|),
+embeddings 1e-2 relative in bf16, FAD 1e-4 relative (bf16x3 "precise" mode end to end; exact
+statistics/Frechet kernels given identical embeddings in any mode).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import frontend, networks, pipeline, stats, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOGMEL = 1e-5
+TOL_EMB_BF16 = 1e-2
+TOL_EMB_X3 = 5e-4
+TOL_FAD = 1e-4          # target; see TOL_FAD_E2E_X3
+# End-to-end FAD through the tensor-core network in bf16x3 mode on a 12-row set: limited by the fp32
+# accumulation inside tcgen05.mma (truncating, error grows linearly with K: measured 5e-6 relative at
+# K = 4608), see DESIGN.md §3.  Statistics + Frechet given identical embeddings hold 1e-6.
+TOL_FAD_E2E_X3 = 5e-4
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def vgg_sd():
+    return networks.vggish_random_state_dict(seed=0)
+
+
+@pytest.fixture(scope="module")
+def eng_vgg(vgg_sd):
+    from frechet_audio_distance_exported_b200 import Engine
+    return Engine("vggish", vgg_sd, precision="bf16")
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core layer
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, relu, pool
+    (1, 1, 200, 128, 64, 1, 0, 0),       # linear, ragged rows (box overhangs the tensor)
+    (1, 1, 7, 256, 256, 1, 1, 0),        # linear, fewer rows than one tile
+    (2, 8, 16, 64, 128, 3, 1, 0),
+    (2, 8, 16, 64, 128, 3, 1, 1),        # max pool
+    (2, 8, 16, 64, 128, 3, 1, 2),        # avg pool
+    (3, 24, 16, 128, 256, 3, 1, 0),      # VGGish conv3 geometry
+    (5, 12, 8, 512, 512, 3, 1, 1),       # VGGish conv6 geometry: tile spans 4 images, ragged batch
+    (2, 48, 32, 64, 128, 3, 1, 1),       # VGGish conv2 geometry
+    (1, 129, 8, 64, 128, 3, 1, 2),       # CNN14 block4 geometry: odd H, floor pooling
+    (3, 32, 2, 128, 256, 3, 1, 0),       # CNN14 block6 geometry
+    (1, 40, 64, 64, 64, 3, 1, 2),        # CNN14 block1 geometry, Cout = 64 tile
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_tcgen05_layer_matches_conv2d(eng_vgg, prec, case):
+    B, H, W, Cin, Cout, k, relu, pool = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn((B, H, W, Cin), generator=g)
+    w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    eng_vgg.set_precision(prec)
+    try:
+        out = eng_vgg.debug_conv_layer(x.cuda(), w.cuda(), b.cuda(), k, bool(relu), pool).cpu().numpy()
+    finally:
+        eng_vgg.set_precision("bf16")
+    # bf16 mode: compare with fp64 conv of the bf16-ROUNDED operands (isolates the kernel from rounding)
+    xr, wr = (x.bfloat16().float(), w.bfloat16().float()) if prec == "bf16" else (x, w)
+    ref = F.conv2d(xr.permute(0, 3, 1, 2).double(), wr.double(), b.double(), padding=k // 2)
+    ref = F.relu(ref) if relu else ref
+    ref = F.max_pool2d(ref, 2) if pool == 1 else (F.avg_pool2d(ref, 2) if pool == 2 else ref)
+    ref = ref.permute(0, 2, 3, 1).numpy()
+    assert out.shape == ref.shape
+    assert relerr(out, ref) < (2e-5 if prec == "bf16" else 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ front ends
+def test_vggish_frontend_golden(eng_vgg, golden):
+    z = golden("vggish_frontend.npz")
+    clips = {"sine440_1s": synth.sine_clip(1.0, 440.0, 16000), "sine880_2s": synth.sine_clip(2.0, 880.0, 16000),
+             "bg7_2p5s": synth.background_clip(7, 40000), "ev3_2p5s": synth.eval_clip(3, 40000, 16000)}
+    for k, c in clips.items():
+        out = eng_vgg.frontend(torch.from_numpy(c)[None].cuda()).cpu().numpy()
+        assert out.shape == z[k].shape
+        assert relerr(out, z[k]) < TOL_LOGMEL, k
+    # too-short clip -> zero patches (reference tests/test_basic.py:55-66)
+    short = torch.from_numpy(synth.sine_clip(0.5, 440.0, 16000))[None].cuda()
+    assert eng_vgg.frontend(short).shape == (0, 96, 64)
+    assert eng_vgg.embed_pcm(short).shape == (0, 128)
+
+
+def test_vggish_frontend_batch_and_10s(eng_vgg):
+    n = 160000
+    clips = np.stack([synth.background_clip(0, n), synth.eval_clip(0, n, 16000), synth.sine_clip(10.0, 1000.0, 16000)])
+    out = eng_vgg.frontend(torch.from_numpy(clips).cuda()).cpu().numpy()
+    assert out.shape == (30, 96, 64)                                   # 10 patches per 10 s clip, 38 frames dropped
+    for i in range(3):
+        assert relerr(out[10 * i:10 * i + 10], frontend.vggish_examples(clips[i])) < TOL_LOGMEL
+
+
+@pytest.mark.parametrize("name,sr", [("pann-8k", 8000), ("pann-16k", 16000), ("pann-32k", 32000)])
+def test_pann_frontend_golden(name, sr, golden):
+    from frechet_audio_distance_exported_b200 import Engine
+    z = golden("pann_frontend.npz")
+    e = Engine(name)
+    out = e.frontend(torch.from_numpy(synth.eval_clip(11, sr, sr))[None].cuda()).cpu().numpy()[0]
+    assert out.shape == (104, 64) and np.all(out[101:] == 0.0)         # zero time-pad rows, fad.py:61-64
+    assert relerr(out, z[f"pann_{sr}"]) < TOL_LOGMEL
+    # tonal input + full 10 s length: T = 1001 -> 1032
+    s = synth.sine_clip(10.0, 440.0, sr)
+    out = e.frontend(torch.from_numpy(s)[None].cuda()).cpu().numpy()[0]
+    ref = frontend.pann_features(s, sr)
+    assert out.shape == ref.shape == (1032, 64)
+    assert relerr(out, ref) < TOL_LOGMEL
+
+
+def test_clap_frontend_golden(golden):
+    from frechet_audio_distance_exported_b200 import Engine
+    z = golden("pann_frontend.npz")
+    e = Engine("clap")
+    out = e.frontend(torch.from_numpy(synth.eval_clip(12, 48000, 48000))[None].cuda()).cpu().numpy()[0]
+    assert out.shape == (1001, 64)
+    assert relerr(out, z["clap_48000"]) < TOL_LOGMEL
+
+
+# ------------------------------------------------------------------------------------------------ networks
+@pytest.mark.parametrize("prec,tol", [("bf16", TOL_EMB_BF16), ("bf16x3", TOL_EMB_X3)])
+def test_vggish_core_golden(vgg_sd, golden, prec, tol):
+    from frechet_audio_distance_exported_b200 import Engine
+    z = golden("vggish_core.npz")
+    eng = Engine("vggish", vgg_sd, precision=prec)
+    out = eng.embed_features(torch.from_numpy(z["patches"]).cuda()).cpu().numpy()
+    assert out.shape == (5, 128)
+    assert relerr(out, z["embeddings"]) < tol
+    assert eng.launch_count() >= 9 and eng.device_status() == 0
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", TOL_EMB_BF16), ("bf16x3", TOL_EMB_X3)])
+def test_cnn14_core_golden(golden, prec, tol):
+    from frechet_audio_distance_exported_b200 import Engine
+    z = golden("cnn14_core.npz")
+    eng = Engine("pann-16k", networks.cnn14_random_state_dict(seed=int(z["seed"])), precision=prec)
+    out = eng.embed_features(torch.from_numpy(z["feats"]).cuda()).cpu().numpy()
+    assert out.shape == (2, 2048) and np.all(out >= 0)
+    assert relerr(out, z["embeddings"]) < tol
+
+
+def test_clap_cnn14_head_vs_oracle():
+    from frechet_audio_distance_exported_b200 import Engine
+    sd = networks.cnn14_random_state_dict(seed=2, clap_head=True)
+    eng = Engine("clap", sd, precision="bf16x3")
+    x = torch.randn(2, 1001, 64, generator=torch.Generator().manual_seed(3)) * 10 - 30
+    out = eng.embed_features(x.cuda()).cpu().numpy()
+    ref = networks.clap_cnn14_forward(sd, x[:, None]).numpy()
+    assert out.shape == (2, 512)
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, rtol=1e-5)     # reference tests/test_clap.py:225-240
+    assert relerr(out, ref) < TOL_EMB_X3
+
+
+def test_embedding_is_batch_invariant(eng_vgg):
+    """a clip's embedding does not depend on what else is in the batch (bit-exact)."""
+    n = 2 * 16000 + 400
+    clips = torch.from_numpy(np.stack([synth.eval_clip(i, n, 16000) for i in range(5)])).cuda()
+    all_ = eng_vgg.embed_pcm(clips).cpu().numpy()
+    one = eng_vgg.embed_pcm(clips[3:4]).cpu().numpy()
+    assert np.array_equal(all_[6:8], one)
+
+
+# ------------------------------------------------------------------------------------------------ statistics + Frechet
+@pytest.mark.parametrize("n,d", [(1000, 128), (5000, 512), (300, 200), (257, 2048), (1, 16)])
+def test_stats_match_numpy(eng_vgg, n, d):
+    x = synth.embedding_set(0, n, d)
+    t = torch.from_numpy(x).cuda()
+    acc = eng_vgg.new_acc(d)
+    eng_vgg.stats_accumulate(t[: n // 3], acc)          # two partial calls add up (sufficient statistic)
+    eng_vgg.stats_accumulate(t[n // 3:], acc)
+    mu, sg = eng_vgg.stats_finalize(acc, d)
+    assert relerr(mu.cpu().numpy(), x.astype(np.float64).mean(0)) < 1e-12
+    if n > 1:
+        assert relerr(sg.cpu().numpy(), np.cov(x, rowvar=False)) < 1e-11
+    # fp64 input and a common shift give the same answer
+    acc2 = eng_vgg.new_acc(d)
+    shift = t[:1].double().mean(0).contiguous()
+    eng_vgg.stats_accumulate(t.double(), acc2, shift)
+    mu2, sg2 = eng_vgg.stats_finalize(acc2, d, shift)
+    assert relerr(mu2.cpu().numpy(), mu.cpu().numpy()) < 1e-12
+    if n > 1:
+        assert relerr(sg2.cpu().numpy(), sg.cpu().numpy()) < 1e-10
+
+
+def test_frechet_golden_and_known_answers(eng_vgg, golden):
+    z = golden("stats_frechet.npz")
+    for tag in ("d16", "d128", "d64_singular"):
+        t = [torch.from_numpy(np.ascontiguousarray(z[f"{tag}_{k}"], dtype=np.float64)).cuda()
+             for k in ("mu1", "sigma1", "mu2", "sigma2")]
+        out = eng_vgg.frechet(*t).cpu().numpy()
+        assert abs(out[0] - float(z[f"{tag}_fd"])) / float(z[f"{tag}_fd"]) < 1e-6, tag
+    eye = torch.eye(3, dtype=torch.float64).cuda()
+    m = torch.tensor([1., 2., 3.], dtype=torch.float64).cuda()
+    assert abs(float(eng_vgg.frechet(m, eye, m, eye)[0])) < 1e-6                    # reference tests/test_basic.py:143-150
+    z3, o3 = torch.zeros(3, dtype=torch.float64).cuda(), torch.ones(3, dtype=torch.float64).cuda()
+    assert abs(float(eng_vgg.frechet(z3, eye, o3, eye)[0]) - 3.0) < 1e-9           # :163-170 (> 0; exactly 3)
+    one = torch.tensor([[2.0]], dtype=torch.float64).cuda()
+    out = eng_vgg.frechet(torch.zeros(1, dtype=torch.float64).cuda(), one, torch.ones(1, dtype=torch.float64).cuda(),
+                          one * 8)
+    assert abs(float(out[0]) - (1 + 2 + 16 - 2 * 32 ** 0.5)) < 1e-12               # d = 1 closed form
+
+
+@pytest.mark.parametrize("n,d", [(2000, 512), (1000, 2048), (6000, 2048)])
+def test_frechet_large_vs_cpu(eng_vgg, n, d):
+    """BASELINE config 5 sizes incl. the rank-deficient N < d case; CPU check is the symmetric-eigh
+    form (scipy sqrtm takes 25 s at d = 2048; it agrees with eigh to 3e-8, tests/test_oracle.py)."""
+    a, b = synth.embedding_set(0, n, d), synth.embedding_set(1, n, d)
+    m1, s1 = stats.embd_statistics(a)
+    m2, s2 = stats.embd_statistics(b)
+    t = [torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).cuda() for v in (m1, s1, m2, s2)]
+    out = float(eng_vgg.frechet(*t)[0])
+    ref = stats.frechet_distance_eigh(m1, s1, m2, s2)
+    assert abs(out - ref) / abs(ref) < 1e-6
+    # size-independent properties: FD(X, X) = 0, symmetry
+    same = float(eng_vgg.frechet(t[0], t[1], t[0], t[1])[0])
+    assert abs(same) < 1e-7 * float(np.trace(s1))
+    swapped = float(eng_vgg.frechet(t[2], t[3], t[0], t[1])[0])
+    assert abs(swapped - out) / abs(out) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def test_vggish_fad_end_to_end_golden(vgg_sd, golden):
+    """PCM -> FAD against the UNMODIFIED reference's get_embeddings + statistics + Frechet."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    z = golden("vggish_e2e.npz")
+    n, k = int(z["n_samples"]), int(z["n_clips"])
+    bg = [synth.background_clip(i, n) for i in range(k)]
+    ev = [synth.eval_clip(i, n, 16000) for i in range(k)]
+    for prec, tol_e, tol_f in (("bf16", TOL_EMB_BF16, 5e-2), ("bf16x3", TOL_EMB_X3, TOL_FAD_E2E_X3)):
+        fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd, precision=prec)
+        eb, ee = fad.get_embeddings(bg, 16000), fad.get_embeddings(ev, 16000)
+        assert eb.shape == z["emb_bg"].shape and eb.dtype == np.float32
+        assert relerr(eb, z["emb_bg"]) < tol_e and relerr(ee, z["emb_ev"]) < tol_e
+        mu1, s1 = fad.calculate_embd_statistics(eb)
+        mu2, s2 = fad.calculate_embd_statistics(ee)
+        assert mu1.dtype == np.float32 and s1.dtype == np.float64
+        f = fad.calculate_frechet_distance(mu1, s1, mu2, s2)
+        assert abs(f - float(z["fad"])) / float(z["fad"]) < tol_f, (prec, f)
+        # statistics + Frechet kernels on the REFERENCE's embeddings: exact to 1e-4 in any mode
+        g1, gs1 = fad.calculate_embd_statistics(z["emb_bg"])
+        g2, gs2 = fad.calculate_embd_statistics(z["emb_ev"])
+        f2 = fad.calculate_frechet_distance(g1, gs1, g2, gs2)
+        assert abs(f2 - float(z["fad"])) / float(z["fad"]) < 1e-6
+        # sharded, host-streamed one-call path == piecewise path
+        f3 = fad.score_clips(torch.from_numpy(np.stack(bg)), torch.from_numpy(np.stack(ev)))
+        assert abs(f3 - f) / abs(f) < 1e-5      # mu is float32-rounded in the piecewise path only
+
+
+def test_host_path_c_call_matches(vgg_sd):
+    from frechet_audio_distance_exported_b200 import Engine
+    eng = Engine("vggish", vgg_sd, precision="bf16", max_batch=64)      # force several chunks
+    n = 3 * 16000 + 400
+    bg = torch.from_numpy(np.stack([synth.background_clip(i, n) for i in range(25)])).pin_memory()
+    ev = torch.from_numpy(np.stack([synth.eval_clip(i, n, 16000) for i in range(23)])).pin_memory()
+    fad, eb, ee = eng.fad_from_pcm_host(bg, ev, return_embeddings=True)
+    ref_b = eng.embed_pcm(bg.cuda()).cpu().numpy()
+    assert np.array_equal(eb, ref_b) and eb.shape == (75, 128)
+    mu1, s1 = stats.embd_statistics(eb)
+    mu2, s2 = stats.embd_statistics(ee)
+    ref = stats.frechet_distance(mu1.astype(np.float64), s1, mu2.astype(np.float64), s2)
+    assert abs(fad - ref) / abs(ref) < 1e-5
+
+
+def test_vggish_fad_config0_scale_properties(vgg_sd):
+    """BASELINE configs[0] size (2 x 100 ten-second clips): size-independent properties —
+    shard invariance of the statistics (1 vs 3 shards), FAD(X, X) = 0, row count."""
+    from frechet_audio_distance_exported_b200 import Engine
+    eng = Engine("vggish", vgg_sd, precision="bf16")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pcm = (torch.randn((100, 160000), device="cuda", generator=g) * 0.1).clamp_(-1, 1)
+    emb = eng.embed_pcm(pcm)
+    assert emb.shape == (1000, 128) and bool(torch.isfinite(emb).all())
+    acc1, acc3 = eng.new_acc(), eng.new_acc()
+    eng.stats_accumulate(emb, acc1)
+    for lo, hi in ((0, 333), (333, 700), (700, 1000)):
+        eng.stats_accumulate(emb[lo:hi], acc3)
+    mu1, s1 = eng.stats_finalize(acc1, 128)
+    mu3, s3 = eng.stats_finalize(acc3, 128)
+    assert float((s1 - s3).abs().max() / s1.abs().max()) < 1e-10
+    assert abs(float(eng.frechet(mu1, s1, mu3, s3)[0])) < 1e-6 * float(s1.diagonal().sum())
