@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libfadb200.so (see include/fadb.h): handle lifetime, weight ingestion,
 // the per-model layer schedules and the host-buffer end-to-end path.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -269,37 +270,99 @@ static inline __nv_bfloat16* lo_plane(fadb_handle* h, int buf, size_t plane_elem
 
 constexpr size_t kVggishActElems = 98304;        // max activation elements per patch (48*32*64)
 
-static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* emb, cudaStream_t st) {
-    const size_t plane = (size_t)h->max_batch * kVggishActElems;
+// tensor-core part of VGGishCore: a1 = conv1 output [P,48,32,64] (hi/lo) -> emb [P,128]
+static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __nv_bfloat16* a1_lo, int64_t P,
+                            float* emb, cudaStream_t st) {
+    const size_t plane = (size_t)h->max_batch * kVggishActElems;            // largest later activation: 24*16*256
     FADB_CHECK(h->ws_act[0].reserve(plane * 2 * sizeof(__nv_bfloat16)));
     FADB_CHECK(h->ws_act[1].reserve(plane * 2 * sizeof(__nv_bfloat16)));
     __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
     __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
     const int B = (int)P;
-    FADB_CHECK(launch_conv1_vggish(h, feats, P, a[0], l[0], st));                       // [P,48,32,64]
     struct Step { int H, W, Cin, pool; };
     static const Step steps[5] = {{48, 32, 64, 1}, {24, 16, 128, 0}, {24, 16, 256, 1}, {12, 8, 256, 0}, {12, 8, 512, 1}};
+    const __nv_bfloat16* in_hi = a1_hi;
+    const __nv_bfloat16* in_lo = a1_lo;
     int cur = 0;
     for (int i = 0; i < 5; ++i) {
         LayerIO io;
-        io.in_hi = a[cur]; io.in_lo = l[cur];
+        io.in_hi = in_hi; io.in_lo = in_lo;
         io.B = B; io.H = steps[i].H; io.W = steps[i].W; io.Cin = steps[i].Cin;
         io.taps = 9; io.relu = 1; io.pool = steps[i].pool;
-        io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+        io.out_hi = a[cur]; io.out_lo = l[cur];
         FADB_CHECK(launch_gemm_layer(h, h->layers[i], io, st));
+        in_hi = a[cur]; in_lo = l[cur];
         cur ^= 1;
     }
     // NHWC flatten (vggish.py:91-94) is the memory order already: [P, 6*4*512]
     static const int fin[3] = {12288, 4096, 4096};
     for (int i = 0; i < 3; ++i) {
         LayerIO io;
-        io.in_hi = a[cur]; io.in_lo = l[cur];
+        io.in_hi = in_hi; io.in_lo = in_lo;
         io.B = 1; io.H = 1; io.W = B; io.Cin = fin[i];
         io.taps = 1; io.relu = (i < 2); io.pool = 0;
-        if (i < 2) { io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1]; }
+        if (i < 2) { io.out_hi = a[cur]; io.out_lo = l[cur]; }
         else io.out_f32 = emb;                                                          // no final ReLU, vggish.py:76-77
         FADB_CHECK(launch_gemm_layer(h, h->layers[5 + i], io, st));
+        in_hi = a[cur]; in_lo = l[cur];
         cur ^= 1;
+    }
+    return FADB_OK;
+}
+
+static int reserve_a1(fadb_handle* h, int buf) {
+    return h->ws_a1[buf].reserve((size_t)h->max_batch * kVggishActElems * 2 * sizeof(__nv_bfloat16));
+}
+static inline __nv_bfloat16* a1_lo_plane(fadb_handle* h, int buf) {
+    return h->ws_a1[buf].as<__nv_bfloat16>() + (size_t)h->max_batch * kVggishActElems;
+}
+
+static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* emb, cudaStream_t st) {
+    FADB_CHECK(reserve_a1(h, 0));
+    __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
+    FADB_CHECK(launch_conv1_vggish(h, feats, P, a1, a1_lo_plane(h, 0), st));           // [P,48,32,64]
+    return vggish_tc_layers(h, a1, a1_lo_plane(h, 0), P, emb, st);
+}
+
+// PCM -> embeddings for VGGish, chunked.  In overlap mode the front end + conv1 (fp64 / fp32 CUDA-core work)
+// of chunk i+1 run on a side stream while the tcgen05 layers of chunk i own the tensor pipes.
+static int vggish_embed_pcm(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                            int64_t rows, float* emb, cudaStream_t st) {
+    const int d = 128;
+    int64_t cpc = h->max_batch / rows;                  // clips per chunk
+    FADB_REQUIRE(cpc >= 1, "max_batch %d smaller than patches per clip %lld", h->max_batch, (long long)rows);
+    const size_t feat_bytes = (size_t)cpc * rows * 96 * 64 * sizeof(float);
+    FADB_CHECK(h->ws_feats.reserve(feat_bytes));
+    const int64_t nchunks = (n_clips + cpc - 1) / cpc;
+    const bool overlap = h->overlap && nchunks > 1;
+    if (!overlap) {
+        for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
+            const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+            FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride,
+                                       h->ws_feats.as<float>(), st));
+            FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
+        }
+        return FADB_OK;
+    }
+    FADB_CHECK(h->ws_feats2.reserve(feat_bytes));
+    FADB_CHECK(reserve_a1(h, 0));
+    FADB_CHECK(reserve_a1(h, 1));
+    float* feats[2] = {h->ws_feats.as<float>(), h->ws_feats2.as<float>()};
+    cudaStream_t aux = h->aux_stream;
+    FADB_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));                 // inputs (and prior use of the workspaces) ordered
+    FADB_CUDA_CHECK(cudaStreamWaitEvent(aux, h->ev_fork, 0));
+    int64_t i = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += cpc, ++i) {
+        const int b = (int)(i & 1);
+        const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
+        __nv_bfloat16* a1 = h->ws_a1[b].as<__nv_bfloat16>();
+        if (i >= 2) FADB_CUDA_CHECK(cudaStreamWaitEvent(aux, h->ev_done[b], 0));      // a1[b] / feats[b] free again
+        FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride, feats[b], aux));
+        FADB_CHECK(launch_conv1_vggish(h, feats[b], nc * rows, a1, a1_lo_plane(h, b), aux));
+        FADB_CUDA_CHECK(cudaEventRecord(h->ev_pre[b], aux));
+        FADB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_pre[b], 0));
+        FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, b), nc * rows, emb + c0 * rows * d, st));
+        FADB_CUDA_CHECK(cudaEventRecord(h->ev_done[b], st));
     }
     return FADB_OK;
 }
@@ -408,6 +471,22 @@ int fadb_create(fadb_handle** out, int device) {
         FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
         FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_compute[i], cudaEventDisableTiming));
     }
+    {
+        // side stream at the LOWEST priority: the tcgen05 layers on the caller's stream get CTAs first,
+        // front-end / conv1 CTAs of the next chunk fill whatever an SM has left
+        int lo = 0, hi = 0;
+        FADB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        int prio = lo;
+        if (const char* e = getenv("FADB_AUX_PRIO")) prio = atoi(e) ? lo : 0;
+        FADB_CUDA_CHECK(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio));
+    }
+    FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+        FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("FADB_OVERLAP")) h->overlap = atoi(e);
+    if (const char* e = getenv("FADB_GEMM_SMEM")) h->gemm_smem_budget = atoi(e);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
     if (rc != FADB_OK) { fadb_destroy(h); return rc; }
@@ -424,6 +503,13 @@ void fadb_destroy(fadb_handle* h) {
     h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    h->ws_feats2.release(); h->ws_a1[0].release(); h->ws_a1[1].release();
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -539,15 +625,7 @@ int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_
     if (rows <= 0) return FADB_OK;       // clips too short: zero rows, like waveform_to_examples -> [0,1,96,64]
     const int d = embed_dim(model);
     if (model == FADB_MODEL_VGGISH) {
-        int64_t cpc = h->max_batch / rows;                  // clips per chunk
-        if (cpc < 1) { set_error("max_batch %d smaller than patches per clip %lld", h->max_batch, (long long)rows); return FADB_E_INVALID; }
-        FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 96 * 64 * sizeof(float)));
-        for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
-            const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
-            FADB_CHECK(launch_frontend(h, model, pcm_dev + c0 * pcm_stride, nc, n_samples, pcm_stride,
-                                       h->ws_feats.as<float>(), st));
-            FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb_dev + c0 * rows * d, st));
-        }
+        FADB_CHECK(vggish_embed_pcm(h, pcm_dev, n_clips, n_samples, pcm_stride, rows, emb_dev, st));
     } else {
         const int64_t cpc = h->max_batch_cnn14;
         FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 64 * sizeof(float)));

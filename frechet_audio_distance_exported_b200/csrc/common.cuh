@@ -93,6 +93,9 @@ struct fadb_handle {
     int precision = FADB_PREC_BF16;
     int max_batch = 2048;           // VGGish patches per internal batch
     int max_batch_cnn14 = 32;       // CNN14 clips per internal batch
+    int gemm_smem_budget = 196608;  // bytes of smem pipeline stages per GEMM CTA (192 KB = own the SM;
+                                    // 144 KB leaves room for a co-resident front-end CTA)
+    int overlap = 0;                // (experiment, default off: measured no gain) run front end + conv1 of chunk i+1 on a side stream under the GEMMs of chunk i
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;
     int64_t launches = 0;
@@ -111,6 +114,12 @@ struct fadb_handle {
     fadb::DevBuf weight_pool;                          // backing store of all packed weights
 
     // activation workspace
+    fadb::DevBuf ws_feats2;     // second feature buffer (overlap mode)
+    fadb::DevBuf ws_a1[2];      // conv1 outputs, double-buffered (overlap mode)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
     fadb::DevBuf ws_feats;      // fp32 features of one batch
     fadb::DevBuf ws_act[2];     // ping-pong bf16 activations (hi plane followed by lo plane)
     fadb::DevBuf ws_misc;       // pooled vectors etc.

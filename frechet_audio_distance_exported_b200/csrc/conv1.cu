@@ -37,20 +37,24 @@ __device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi,
 }
 
 // ---------------------------------------------------------------- VGGish: conv + ReLU + maxpool
-// grid = (24 pooled-row pairs, P patches); block = 256 = 64 pooled pixels x 4 channel groups of 16
-__global__ void __launch_bounds__(256) conv1_vggish_kernel(const float* __restrict__ feats, const float* __restrict__ w,
+// grid = (6 bands of 8 pooled rows, P patches); block = 256 = 64 pooled pixels x 4 channel groups of 16.
+// The 18 input rows of the band (16 + halo), the 9x64 weights and the bias are staged once per CTA and
+// reused by 4 iterations of 2 pooled rows each.
+constexpr int kC1Band = 8;                       // pooled rows per CTA
+__global__ void __launch_bounds__(256, 2) conv1_vggish_kernel(const float* __restrict__ feats, const float* __restrict__ w,
                                                            const float* __restrict__ bias,
                                                            __nv_bfloat16* __restrict__ out_hi,
                                                            __nv_bfloat16* __restrict__ out_lo) {
     constexpr int H = 96, W = 64, HP = 48, WP = 32;
-    __shared__ float s_in[6][W + 2];
+    constexpr int ROWS = 2 * kC1Band + 2;
+    __shared__ float s_in[ROWS][W + 2];
     __shared__ __align__(16) float s_w[9][64];
     __shared__ float s_b[64];
     const int patch = blockIdx.y;
-    const int prow0 = blockIdx.x * 2;           // first pooled row of this CTA
-    const int y_in0 = prow0 * 2 - 1;            // first input row staged (with halo)
+    const int prow_base = blockIdx.x * kC1Band;     // first pooled row of this CTA
+    const int y_in0 = prow_base * 2 - 1;            // first input row staged (with halo)
     const float* src = feats + size_t(patch) * H * W;
-    for (int i = threadIdx.x; i < 6 * (W + 2); i += 256) {
+    for (int i = threadIdx.x; i < ROWS * (W + 2); i += 256) {
         const int r = i / (W + 2), c = i % (W + 2);
         const int y = y_in0 + r, x = c - 1;
         s_in[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + y * W + x) : 0.f;
@@ -60,46 +64,50 @@ __global__ void __launch_bounds__(256) conv1_vggish_kernel(const float* __restri
     __syncthreads();
 
     const int g = threadIdx.x & 3;              // channel group
-    const int pp = threadIdx.x >> 2;            // pooled pixel in the CTA: 0..63
+    const int pp = threadIdx.x >> 2;            // pooled pixel within an iteration: 0..63
     const int pr = pp >> 5, pc = pp & 31;
-    float in[4][4];
+#pragma unroll 1
+    for (int itr = 0; itr < kC1Band / 2; ++itr) {
+        const int lr = itr * 2 + pr;            // pooled row within the band
+        float acc[4][16];                       // 4 positions of the pooling window x 16 channels
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) in[r][c] = s_in[pr * 2 + r][pc * 2 + c];
-
-    // tap-outer loop: 16 weights are loaded once per tap and reused by the 4 positions of the pooling window
-    float acc[4][16];
+            for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {
+            // the two input rows this kernel row touches, 4 columns each (8-byte aligned pairs)
+            const float2 r0a = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky][pc * 2]);
+            const float2 r0b = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky][pc * 2 + 2]);
+            const float2 r1a = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky + 1][pc * 2]);
+            const float2 r1b = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky + 1][pc * 2 + 2]);
+            const float in0[4] = {r0a.x, r0a.y, r0b.x, r0b.y};
+            const float in1[4] = {r1a.x, r1a.y, r1b.x, r1b.y};
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4* wp = reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][g * 16]);
+                float wv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
+                for (int v = 0; v < 4; ++v) {
+                    const float4 t = wp[v];
+                    wv[v * 4 + 0] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w;
+                }
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const float4* wp = reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][g * 16]);
-            float wv[16];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float4 t = wp[v];
-                wv[v * 4 + 0] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float xv = in[(q >> 1) + ky][(q & 1) + kx];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[q][j] = fmaf(xv, wv[j], acc[q][j]);
+                for (int j = 0; j < 16; ++j) {
+                    acc[0][j] = fmaf(in0[kx], wv[j], acc[0][j]);
+                    acc[1][j] = fmaf(in0[kx + 1], wv[j], acc[1][j]);
+                    acc[2][j] = fmaf(in1[kx], wv[j], acc[2][j]);
+                    acc[3][j] = fmaf(in1[kx + 1], wv[j], acc[3][j]);
+                }
             }
         }
-    float best[16];
+        float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) best[j] = fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j]));
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(best[j] + s_b[g * 16 + j], 0.f);   // relu(max(.)+b) == max(relu(.+b))
-    const size_t o = ((size_t(patch) * HP + prow0 + pr) * WP + pc) * 64 + g * 16;
-    store16(v, out_hi, out_lo, o);
+        for (int j = 0; j < 16; ++j)            // relu(max(.)+b) == max(relu(.+b))
+            v[j] = fmaxf(fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j])) + s_b[g * 16 + j], 0.f);
+        const size_t o = ((size_t(patch) * HP + prow_base + lr) * WP + pc) * 64 + g * 16;
+        store16(v, out_hi, out_lo, o);
+    }
 }
 
 // ---------------------------------------------------------------- CNN14: bn0 + conv + BN + ReLU
@@ -159,7 +167,7 @@ int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, _
                         __nv_bfloat16* out_lo, cudaStream_t st) {
     if (n_patches <= 0) return FADB_OK;
     FADB_REQUIRE(n_patches <= 65535, "conv1: at most 65535 patches per batch");
-    dim3 grid(24, (unsigned)n_patches);
+    dim3 grid(48 / kC1Band, (unsigned)n_patches);
     conv1_vggish_kernel<<<grid, 256, 0, st>>>(feats, h->conv1_w, h->conv1_b, out_hi,
                                              h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);
     h->launches++;

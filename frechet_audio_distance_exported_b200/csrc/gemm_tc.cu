@@ -43,6 +43,9 @@ struct GemmParams {
     int taps;             // 9 or 1
     int npass;            // 1 (bf16) or 3 (bf16x3)
     int N;                // Cout
+    int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
+    int kb_begin, kb_end; // K-block range of this launch (whole K unless the exact-accumulation path splits it)
+    int raw;              // 0 = fused epilogue; 1 = write raw fp32 partial sums; 2 = add them to out_f32
     int relu;
     int pool;             // 0 none, 1 max, 2 avg
     int Ho, Wo;           // output spatial dims (after pooling)
@@ -62,9 +65,16 @@ template <int BN>
 struct GemmCfg {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kMaxStages = 8;
     static constexpr int kTmemCols = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
-    static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr int kExtraBytes = 256 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr int kMaxSmemBytes = 4 * 49152 + kExtraBytes;     // 192 KB of stages at most
+    static int stages_for(int budget_bytes) {
+        int s = budget_bytes / kStageBytes;
+        if (s > kMaxStages) s = kMaxStages;
+        if (s < 2) s = 2;
+        return s;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -196,7 +206,7 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
-    constexpr int kStages = Cfg::kStages;
+    const int kStages = p.stages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-B alignment
@@ -237,7 +247,6 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int nk = p.npass * p.taps * p.cin_blocks;                  // K blocks per tile
     const int kb_per_pass = p.taps * p.cin_blocks;
 
     if (warp == 0) {
@@ -252,22 +261,22 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 const int ht = m % p.tiles_h;
                 const int bt = m / p.tiles_h;
                 const int x0 = wt * p.BW, y0 = ht * p.BH, b0 = bt * p.BB;
-                for (int pass = 0; pass < p.npass; ++pass) {
+                for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg) {
+                    const int pass = kbg / kb_per_pass;
+                    const int kb = kbg - pass * kb_per_pass;
                     const CUtensorMap* ta = &p.tmA[pass == 1 ? 1 : 0];
                     const CUtensorMap* tb = &p.tmB[pass == 2 ? 1 : 0];
-                    for (int kb = 0; kb < kb_per_pass; ++kb) {
-                        const int tap = kb / p.cin_blocks;
-                        const int cb = kb - tap * p.cin_blocks;
-                        int dy = 0, dx = 0;
-                        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
-                        const uint32_t sa = base + stage * Cfg::kStageBytes;
-                        const uint32_t sb = sa + kABytes;
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
-                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                        tma_load_2d(tb, bar_full + 8 * stage, sb, kb * kBlockK, n0);
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                    }
+                    const int tap = kb / p.cin_blocks;
+                    const int cb = kb - tap * p.cin_blocks;
+                    int dy = 0, dx = 0;
+                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
+                    const uint32_t sa = base + stage * Cfg::kStageBytes;
+                    const uint32_t sb = sa + kABytes;
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+                    tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                    tma_load_2d(tb, bar_full + 8 * stage, sb, kb * kBlockK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);    // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // TMA bytes landed
                     tc_fence_after();
                     const uint32_t sa = base + stage * Cfg::kStageBytes;
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_empty + 8 * stage);                     // frees the smem stage when MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             const int x = wt * p.BW + ww, y = ht * p.BH + hh, b = bt * p.BB + bb;
             bool valid;
             size_t obase;
-            if (p.pool) {
+            if (p.pool && !p.raw) {
                 const int px = x >> 1, py = y >> 1;
                 valid = pool_lane && px < p.Wo && py < p.Ho && b < p.B;
                 obase = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + n0;
@@ -353,6 +362,24 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
                 }
                 float v[32];
+                if (p.raw) {
+                    // exact-accumulation path: un-biased fp32 partial sums of this K segment, summed in fp32
+                    // round-to-nearest across segments (the tensor core's own accumulation truncates)
+                    if (valid) {
+                        float4* d = reinterpret_cast<float4*>(p.out_f32 + obase + c * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 t = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            if (p.raw == 2) {
+                                const float4 o4 = d[q];
+                                t.x += o4.x; t.y += o4.y; t.z += o4.z; t.w += o4.w;
+                            }
+                            d[q] = t;
+                        }
+                    }
+                    continue;
+                }
                 if (p.bias) {
                     const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
 #pragma unroll
@@ -427,6 +454,71 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Finishing kernel of the exact-accumulation path: raw fp32 sums [B,H,W,N] -> +bias -> ReLU -> 2x2 pool
+// -> bf16 hi/lo (or fp32).  One thread per (output pixel, 8 channels).
+// ------------------------------------------------------------------------------------------------
+constexpr int kExactSegment = 16;   // K-blocks (= 64 MMAs of K = 16) per accumulation chain
+
+__global__ void __launch_bounds__(256) finish_layer_kernel(const float* __restrict__ raw, int B, int H, int W, int N,
+                                                           const float* __restrict__ bias, int relu, int pool,
+                                                           __nv_bfloat16* __restrict__ out_hi,
+                                                           __nv_bfloat16* __restrict__ out_lo,
+                                                           float* __restrict__ out_f32) {
+    const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+    const int ng = N / 8;
+    const size_t items = size_t(B) * Ho * Wo * ng;
+    for (size_t it = blockIdx.x * size_t(blockDim.x) + threadIdx.x; it < items; it += size_t(gridDim.x) * blockDim.x) {
+        const int g = int(it % ng);
+        size_t px = it / ng;
+        const int x = int(px % Wo); px /= Wo;
+        const int y = int(px % Ho);
+        const int b = int(px / Ho);
+        float bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = bias ? __ldg(bias + g * 8 + j) : 0.f;
+        float v[8];
+        auto load = [&](int yy, int xx, float (&t)[8]) {
+            const float4* s4 = reinterpret_cast<const float4*>(raw + ((size_t(b) * H + yy) * W + xx) * N + g * 8);
+            const float4 a = s4[0], c = s4[1];
+            t[0] = a.x + bv[0]; t[1] = a.y + bv[1]; t[2] = a.z + bv[2]; t[3] = a.w + bv[3];
+            t[4] = c.x + bv[4]; t[5] = c.y + bv[5]; t[6] = c.z + bv[6]; t[7] = c.w + bv[7];
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], 0.f);
+            }
+        };
+        if (!pool) {
+            load(y, x, v);
+        } else {
+            float t0[8], t1[8], t2[8], t3[8];
+            load(2 * y, 2 * x, t0); load(2 * y, 2 * x + 1, t1); load(2 * y + 1, 2 * x, t2); load(2 * y + 1, 2 * x + 1, t3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = pool == 1 ? fmaxf(fmaxf(t0[j], t1[j]), fmaxf(t2[j], t3[j])) : ((t0[j] + t1[j]) + (t2[j] + t3[j])) * 0.25f;
+        }
+        const size_t o = ((size_t(b) * Ho + y) * Wo + x) * N + g * 8;
+        if (out_f32) {
+            float4* d = reinterpret_cast<float4*>(out_f32 + o);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]);
+            d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            uint4 hi;
+            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(out_hi + o) = hi;
+            if (out_lo) {
+                uint4 lo;
+                lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+                lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+                lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+                lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+                *reinterpret_cast<uint4*>(out_lo + o) = lo;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -447,11 +539,11 @@ int gemm_init(fadb_handle* h) {
         g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<64>::kSmemBytes));
+                                         GemmCfg<64>::kMaxSmemBytes));
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<128>::kSmemBytes));
+                                         GemmCfg<128>::kMaxSmemBytes));
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<256>::kSmemBytes));
+                                         GemmCfg<256>::kMaxSmemBytes));
     return FADB_OK;
 }
 
@@ -571,10 +663,53 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         FADB_CUDA_CHECK(cudaEventCreate(&ev1));
         FADB_CUDA_CHECK(cudaEventRecord(ev0, st));
     }
-    if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, GemmCfg<256>::kSmemBytes, st>>>(p);
-    else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, GemmCfg<128>::kSmemBytes, st>>>(p);
-    else fadb_gemm_tc_kernel<64><<<grid, kThreads, GemmCfg<64>::kSmemBytes, st>>>(p);
-    h->launches++;
+    const int budget = h->gemm_smem_budget;
+    auto launch = [&](const GemmParams& q) {
+        GemmParams pp = q;
+        if (BN == 256) {
+            pp.stages = GemmCfg<256>::stages_for(budget);
+            fadb_gemm_tc_kernel<256><<<grid, kThreads, pp.stages * GemmCfg<256>::kStageBytes + GemmCfg<256>::kExtraBytes, st>>>(pp);
+        } else if (BN == 128) {
+            pp.stages = GemmCfg<128>::stages_for(budget);
+            fadb_gemm_tc_kernel<128><<<grid, kThreads, pp.stages * GemmCfg<128>::kStageBytes + GemmCfg<128>::kExtraBytes, st>>>(pp);
+        } else {
+            pp.stages = GemmCfg<64>::stages_for(budget);
+            fadb_gemm_tc_kernel<64><<<grid, kThreads, pp.stages * GemmCfg<64>::kStageBytes + GemmCfg<64>::kExtraBytes, st>>>(pp);
+        }
+        h->launches++;
+    };
+    const int nk = npass * io.taps * p.cin_blocks;
+    if (npass == 1) {
+        p.kb_begin = 0;
+        p.kb_end = nk;
+        p.raw = 0;
+        launch(p);
+    } else {
+        // bf16x3 "exact accumulation": the fp32 accumulator inside tcgen05.mma truncates (error grows linearly
+        // with the chain length: 5e-6 relative at K = 4608), so K is cut into segments of kExactSegment
+        // K-blocks; each launch leaves raw fp32 partial sums, added in fp32 round-to-nearest, and a small
+        // finishing kernel applies bias / ReLU / pooling and the hi/lo split.
+        const size_t scratch_elems = size_t(io.B) * io.H * io.W * L.N;
+        FADB_CHECK(h->ws_misc.reserve(scratch_elems * sizeof(float)));
+        GemmParams q = p;
+        q.out_f32 = h->ws_misc.as<float>();
+        q.out_hi = nullptr; q.out_lo = nullptr;
+        q.Ho = io.H; q.Wo = io.W;
+        int seg = 0;
+        for (int k0 = 0; k0 < nk; k0 += kExactSegment, ++seg) {
+            q.kb_begin = k0;
+            q.kb_end = (k0 + kExactSegment < nk) ? k0 + kExactSegment : nk;
+            q.raw = seg == 0 ? 1 : 2;
+            launch(q);
+        }
+        const size_t out_px = size_t(io.B) * p.Ho * p.Wo;
+        const size_t items = out_px * (L.N / 8);
+        int fg = (int)((items + 255) / 256);
+        if (fg > 148 * 16) fg = 148 * 16;
+        finish_layer_kernel<<<fg, 256, 0, st>>>(h->ws_misc.as<float>(), io.B, io.H, io.W, L.N, L.bias, io.relu, io.pool,
+                                                 p.out_hi, p.out_lo, p.out_f32);
+        h->launches++;
+    }
     if (h->profile) {
         FADB_CUDA_CHECK(cudaEventRecord(ev1, st));
         h->prof_events.push_back(ev0);

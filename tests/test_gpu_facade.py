@@ -119,7 +119,7 @@ def test_pann_preprocessing_to_model(name, sr):
     out = fad.get_embeddings(clips, sr)
     assert out.shape == (3, 2048) and np.all(out >= 0)
     ref = ora.get_embeddings(clips)
-    assert np.max(np.abs(out - ref)) / np.max(np.abs(ref)) < 5e-4
+    assert np.max(np.abs(out - ref)) / np.max(np.abs(ref)) < 1e-4
     out2 = fad.model(torch.randn(2, 1, 200, 64))                           # tests/test_pann.py:131-143 (any T)
     assert out2.shape == (2, 2048)
 
@@ -135,7 +135,7 @@ def test_clap_facade():
     assert e1.shape == (1, 512) and np.array_equal(e1, e2)
     np.testing.assert_allclose(np.linalg.norm(e1, axis=1), 1.0, rtol=1e-5)
     ref = pipeline.OracleFAD("clap", sd).embed_clip(a)
-    assert np.max(np.abs(e1 - ref)) / np.max(np.abs(ref)) < 5e-4
+    assert np.max(np.abs(e1 - ref)) / np.max(np.abs(ref)) < 1e-4
     bg = [synth.sine_clip(1.0, 440.0 + 10 * i, 48000) for i in range(5)]
     ev = [synth.sine_clip(1.0, 880.0 + 10 * i, 48000) for i in range(5)]
     mu1, s1 = fad.calculate_embd_statistics(fad.get_embeddings(bg, 48000))
