@@ -487,6 +487,7 @@ int fadb_create(fadb_handle** out, int device) {
     }
     if (const char* e = getenv("FADB_OVERLAP")) h->overlap = atoi(e);
     if (const char* e = getenv("FADB_GEMM_SMEM")) h->gemm_smem_budget = atoi(e);
+    if (const char* e = getenv("FADB_RESIDENT_B")) h->resident_b = atoi(e);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
     if (rc != FADB_OK) { fadb_destroy(h); return rc; }

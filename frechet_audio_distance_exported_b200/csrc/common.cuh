@@ -93,8 +93,9 @@ struct fadb_handle {
     int precision = FADB_PREC_BF16;
     int max_batch = 2048;           // VGGish patches per internal batch
     int max_batch_cnn14 = 32;       // CNN14 clips per internal batch
-    int gemm_smem_budget = 196608;  // bytes of smem pipeline stages per GEMM CTA (192 KB = own the SM;
-                                    // 144 KB leaves room for a co-resident front-end CTA)
+    int gemm_smem_budget = 231168;  // bytes of smem for resident weights + pipeline stages per GEMM CTA
+                                    // (227 KB opt-in maximum minus barriers/alignment slack)
+    int resident_b = 1;             // keep short-K weight slabs resident in smem (see gemm_tc.cu)
     int overlap = 0;                // (experiment, default off: measured no gain) run front end + conv1 of chunk i+1 on a side stream under the GEMMs of chunk i
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;

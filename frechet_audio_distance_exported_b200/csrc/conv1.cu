@@ -17,6 +17,23 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 __device__ __forceinline__ float bfr(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// Packed fp32x2 FMA (sm_100+): d.lo = a.lo*b.lo + c.lo, d.hi = a.hi*b.hi + c.hi in ONE issue slot.  A 3-register
+// scalar FFMA issues every other cycle per scheduler on Blackwell, so the packed form is what reaches the
+// 128-lane fp32 rate in an FMA-bound loop.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi, __nv_bfloat16* lo, size_t o) {
     uint4 a, b;
     a.x = pack2(v[0], v[1]); a.y = pack2(v[2], v[3]); a.z = pack2(v[4], v[5]); a.w = pack2(v[6], v[7]);
@@ -37,19 +54,21 @@ __device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi,
 }
 
 // ---------------------------------------------------------------- VGGish: conv + ReLU + maxpool
-// grid = (6 bands of 8 pooled rows, P patches); block = 256 = 64 pooled pixels x 4 channel groups of 16.
-// The 18 input rows of the band (16 + halo), the 9x64 weights and the bias are staged once per CTA and
-// reused by 4 iterations of 2 pooled rows each.
+// grid = (6 bands of 8 pooled rows, P patches); block = 256 threads = the 8 x 32 pooled pixels of the band.
+// A thread owns ONE pooled pixel (its 4x4 input window lives in registers as packed f32x2 pairs) and loops
+// over the 64 output channels in 4 groups of 16.  The weight address is therefore warp-uniform: every
+// LDS.128 of weights is a single broadcast wavefront (the first version indexed weights by lane and was
+// shared-memory-bandwidth bound: 85 % LSU wavefront utilisation, ncu r01).
 constexpr int kC1Band = 8;                       // pooled rows per CTA
 __global__ void __launch_bounds__(256, 2) conv1_vggish_kernel(const float* __restrict__ feats, const float* __restrict__ w,
-                                                           const float* __restrict__ bias,
-                                                           __nv_bfloat16* __restrict__ out_hi,
-                                                           __nv_bfloat16* __restrict__ out_lo) {
+                                                              const float* __restrict__ bias,
+                                                              __nv_bfloat16* __restrict__ out_hi,
+                                                              __nv_bfloat16* __restrict__ out_lo) {
     constexpr int H = 96, W = 64, HP = 48, WP = 32;
     constexpr int ROWS = 2 * kC1Band + 2;
-    __shared__ float s_in[ROWS][W + 2];
+    __shared__ __align__(16) float s_in[ROWS][W + 4];      // pitch 68: rows stay 16-byte aligned
     __shared__ __align__(16) float s_w[9][64];
-    __shared__ float s_b[64];
+    __shared__ __align__(16) float s_b[64];
     const int patch = blockIdx.y;
     const int prow_base = blockIdx.x * kC1Band;     // first pooled row of this CTA
     const int y_in0 = prow_base * 2 - 1;            // first input row staged (with halo)
@@ -63,72 +82,81 @@ __global__ void __launch_bounds__(256, 2) conv1_vggish_kernel(const float* __res
     if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
 
-    const int g = threadIdx.x & 3;              // channel group
-    const int pp = threadIdx.x >> 2;            // pooled pixel within an iteration: 0..63
-    const int pr = pp >> 5, pc = pp & 31;
+    const int lr = threadIdx.x >> 5;            // pooled row within the band (= warp)
+    const int pc = threadIdx.x & 31;            // pooled column (= lane)
+    // 4x4 input window, each value duplicated into both halves of an f32x2 register
+    unsigned long long in[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float2 a = *reinterpret_cast<const float2*>(&s_in[lr * 2 + r][pc * 2]);
+        const float2 b = *reinterpret_cast<const float2*>(&s_in[lr * 2 + r][pc * 2 + 2]);
+        in[r][0] = pack_f32x2(a.x, a.x); in[r][1] = pack_f32x2(a.y, a.y);
+        in[r][2] = pack_f32x2(b.x, b.x); in[r][3] = pack_f32x2(b.y, b.y);
+    }
+    const size_t obase = ((size_t(patch) * HP + prow_base + lr) * WP + pc) * 64;
+
 #pragma unroll 1
-    for (int itr = 0; itr < kC1Band / 2; ++itr) {
-        const int lr = itr * 2 + pr;            // pooled row within the band
-        float acc[4][16];                       // 4 positions of the pooling window x 16 channels
+    for (int g = 0; g < 4; ++g) {               // 16 output channels per pass
+        unsigned long long acc[4][8];           // 4 positions of the pooling window x 8 channel PAIRS
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
-#pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky) {
-            // the two input rows this kernel row touches, 4 columns each (8-byte aligned pairs)
-            const float2 r0a = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky][pc * 2]);
-            const float2 r0b = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky][pc * 2 + 2]);
-            const float2 r1a = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky + 1][pc * 2]);
-            const float2 r1b = *reinterpret_cast<const float2*>(&s_in[lr * 2 + ky + 1][pc * 2 + 2]);
-            const float in0[4] = {r0a.x, r0a.y, r0b.x, r0b.y};
-            const float in1[4] = {r1a.x, r1a.y, r1b.x, r1b.y};
+            for (int j = 0; j < 8; ++j) acc[q][j] = 0ull;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float4* wp = reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][g * 16]);
-                float wv[16];
+                const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(&s_w[ky * 3 + kx][g * 16]);   // warp-uniform
+                unsigned long long wv[8];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    const float4 t = wp[v];
-                    wv[v * 4 + 0] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w;
+                    const ulonglong2 t = wp[v];
+                    wv[v * 2 + 0] = t.x;
+                    wv[v * 2 + 1] = t.y;
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    acc[0][j] = fmaf(in0[kx], wv[j], acc[0][j]);
-                    acc[1][j] = fmaf(in0[kx + 1], wv[j], acc[1][j]);
-                    acc[2][j] = fmaf(in1[kx], wv[j], acc[2][j]);
-                    acc[3][j] = fmaf(in1[kx + 1], wv[j], acc[3][j]);
+                for (int j = 0; j < 8; ++j) {
+                    acc[0][j] = ffma2(in[ky][kx], wv[j], acc[0][j]);
+                    acc[1][j] = ffma2(in[ky][kx + 1], wv[j], acc[1][j]);
+                    acc[2][j] = ffma2(in[ky + 1][kx], wv[j], acc[2][j]);
+                    acc[3][j] = ffma2(in[ky + 1][kx + 1], wv[j], acc[3][j]);
                 }
             }
-        }
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)            // relu(max(.)+b) == max(relu(.+b))
-            v[j] = fmaxf(fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j])) + s_b[g * 16 + j], 0.f);
-        const size_t o = ((size_t(patch) * HP + prow_base + lr) * WP + pc) * 64 + g * 16;
-        store16(v, out_hi, out_lo, o);
+        for (int j = 0; j < 8; ++j) {           // relu(max(.)+b) == max(relu(.+b))
+            float a0, a1, b0, b1, c0, c1, d0, d1;
+            unpack_f32x2(acc[0][j], a0, a1); unpack_f32x2(acc[1][j], b0, b1);
+            unpack_f32x2(acc[2][j], c0, c1); unpack_f32x2(acc[3][j], d0, d1);
+            const float2 bb = *reinterpret_cast<const float2*>(&s_b[g * 16 + 2 * j]);
+            v[2 * j] = fmaxf(fmaxf(fmaxf(a0, b0), fmaxf(c0, d0)) + bb.x, 0.f);
+            v[2 * j + 1] = fmaxf(fmaxf(fmaxf(a1, b1), fmaxf(c1, d1)) + bb.y, 0.f);
+        }
+        store16(v, out_hi, out_lo, obase + g * 16);
     }
 }
 
 // ---------------------------------------------------------------- CNN14: bn0 + conv + BN + ReLU
-// grid = (T rows, B clips); block = 256 = 64 mel columns x 4 channel groups of 16
-__global__ void __launch_bounds__(256) conv1_cnn14_kernel(const float* __restrict__ feats, int T,
-                                                          const float* __restrict__ bn0_scale,
-                                                          const float* __restrict__ bn0_shift,
-                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                          __nv_bfloat16* __restrict__ out_hi,
-                                                          __nv_bfloat16* __restrict__ out_lo) {
+// grid = (ceil(T / 4) row bands, B clips); block = 256 threads = 4 time rows x 64 mel columns, one pixel each;
+// output channels in 4 groups of 16 with warp-uniform (broadcast) weight loads, packed f32x2 FMAs.
+constexpr int kC14Rows = 4;
+__global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __restrict__ feats, int T,
+                                                             const float* __restrict__ bn0_scale,
+                                                             const float* __restrict__ bn0_shift,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             __nv_bfloat16* __restrict__ out_hi,
+                                                             __nv_bfloat16* __restrict__ out_lo) {
     constexpr int W = 64;
-    __shared__ float s_in[3][W + 2];
+    __shared__ float s_in[kC14Rows + 2][W + 2];
     __shared__ __align__(16) float s_w[9][64];
-    __shared__ float s_b[64];
+    __shared__ __align__(16) float s_b[64];
     const int clip = blockIdx.y;
-    const int y0 = blockIdx.x;
+    const int y0 = blockIdx.x * kC14Rows;
     const float* src = feats + size_t(clip) * T * W;
-    for (int i = threadIdx.x; i < 3 * (W + 2); i += 256) {
+    for (int i = threadIdx.x; i < (kC14Rows + 2) * (W + 2); i += 256) {
         const int r = i / (W + 2), c = i % (W + 2);
         const int y = y0 - 1 + r, x = c - 1;
-        float v = 0.f;
+        float v = 0.f;      // conv zero padding happens AFTER bn0 (pann.py:249-255), so it stays a literal 0
         if (y >= 0 && y < T && x >= 0 && x < W) v = fmaf(__ldg(src + y * W + x), bn0_scale[x], bn0_shift[x]);
         s_in[r][c] = v;
     }
@@ -136,31 +164,47 @@ __global__ void __launch_bounds__(256) conv1_cnn14_kernel(const float* __restric
     if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
 
-    const int g = threadIdx.x & 3;
-    const int x = threadIdx.x >> 2;
-    float acc[16];
+    const int ry = threadIdx.x >> 6;            // row within the band
+    const int x = threadIdx.x & 63;
+    const int y = y0 + ry;
+    if (y >= T) return;
+    unsigned long long in[3][3];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const float xv = s_in[ky][x + kx];
-            const float4* wp = reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][g * 16]);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float4 wv = wp[v];
-                acc[v * 4 + 0] = fmaf(xv, wv.x, acc[v * 4 + 0]);
-                acc[v * 4 + 1] = fmaf(xv, wv.y, acc[v * 4 + 1]);
-                acc[v * 4 + 2] = fmaf(xv, wv.z, acc[v * 4 + 2]);
-                acc[v * 4 + 3] = fmaf(xv, wv.w, acc[v * 4 + 3]);
-            }
+        for (int c = 0; c < 3; ++c) {
+            const float v = s_in[ry + r][x + c];
+            in[r][c] = pack_f32x2(v, v);
         }
-    float v[16];
+    const size_t obase = ((size_t(clip) * T + y) * W + x) * 64;
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        unsigned long long acc[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(acc[j] + s_b[g * 16 + j], 0.f);
-    const size_t o = ((size_t(clip) * T + y0) * W + x) * 64 + g * 16;
-    store16(v, out_hi, out_lo, o);
+        for (int j = 0; j < 8; ++j) acc[j] = 0ull;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(&s_w[ky * 3 + kx][g * 16]);   // warp-uniform
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const ulonglong2 t = wp[v];
+                    acc[2 * v] = ffma2(in[ky][kx], t.x, acc[2 * v]);
+                    acc[2 * v + 1] = ffma2(in[ky][kx], t.y, acc[2 * v + 1]);
+                }
+            }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a0, a1;
+            unpack_f32x2(acc[j], a0, a1);
+            const float2 bb = *reinterpret_cast<const float2*>(&s_b[g * 16 + 2 * j]);
+            v[2 * j] = fmaxf(a0 + bb.x, 0.f);
+            v[2 * j + 1] = fmaxf(a1 + bb.y, 0.f);
+        }
+        store16(v, out_hi, out_lo, obase + g * 16);
+    }
 }
 
 int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, __nv_bfloat16* out_hi,
@@ -179,7 +223,7 @@ int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int 
                        __nv_bfloat16* out_lo, cudaStream_t st) {
     if (n_clips <= 0) return FADB_OK;
     FADB_REQUIRE(n_clips <= 65535, "conv1: at most 65535 clips per batch");
-    dim3 grid((unsigned)T, (unsigned)n_clips);
+    dim3 grid((unsigned)((T + kC14Rows - 1) / kC14Rows), (unsigned)n_clips);
     conv1_cnn14_kernel<<<grid, 256, 0, st>>>(feats, T, h->bn0_scale, h->bn0_shift, h->conv1_w, h->conv1_b, out_hi,
                                             h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);
     h->launches++;

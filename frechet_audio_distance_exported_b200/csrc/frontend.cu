@@ -58,11 +58,53 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
+// FFT buffer index padding: one 16-byte slot every 8 complex values, so that the stride-4 / stride-16
+// scatter of the early Stockham passes spreads over all shared-memory banks (ncu r01: the unpadded version
+// was shared-memory-bandwidth bound, 83 % LSU wavefront utilisation, 63 M bank-conflict wavefronts).
+__device__ __forceinline__ int pidx(int n) { return n + (n >> 3); }
+
+// Per-pass twiddle tables in shared memory, laid out [pass][butterfly q][r-1][lane]: a warp's twiddle load is
+// 32 consecutive 16-byte slots (conflict-free) instead of a strided gather from the exp(-2 pi i k/NF) table
+// (16-way bank conflicts at stride NF/64).
+template <int M>
+struct FftPlan {
+    // passes after the first (the first has all twiddles = 1)
+    static constexpr int kPasses = (M == 256) ? 3 : 4;                 // M=128: 4,4,2 ; M=256: 4,4,4 ; M=512: 4,4,4,2
+    static constexpr int radix(int i) { return (M == 256) ? 4 : (i == 2 + (M == 512) ? 2 : 4); }
+    static constexpr int per(int i) { return ((M / radix(i)) + 31) / 32; }
+    static constexpr int offset(int i) {                                // in units of 32 double2
+        int o = 0;
+        for (int j = 0; j < i; ++j) o += per(j) * (radix(j) - 1);
+        return o;
+    }
+    static constexpr int kSlots = offset(kPasses) * 32;                 // double2 entries
+};
+
+template <int M, int NF>
+__device__ __forceinline__ void build_pass_twiddles(double2* __restrict__ ptw, const double2* __restrict__ tw_global) {
+    using P = FftPlan<M>;
+    int pp = 4;
+#pragma unroll
+    for (int ps = 0; ps < P::kPasses; ++ps) {
+        const int R = P::radix(ps), PER = P::per(ps), T = M / R;
+        const int tstep = NF / (pp * R);
+        for (int e = threadIdx.x; e < PER * (R - 1) * 32; e += blockDim.x) {
+            const int lane = e & 31;
+            const int r = (e >> 5) % (R - 1) + 1;
+            const int q = (e >> 5) / (R - 1);
+            const int i = lane + 32 * q;
+            double2 v = make_double2(1.0, 0.0);
+            if (i < T) v = tw_global[r * (i & (pp - 1)) * tstep];
+            ptw[P::offset(ps) * 32 + e] = v;
+        }
+        pp *= R;
+    }
+}
+
 // One in-place Stockham pass of radix R over the warp's M-point buffer: every lane first pulls ALL of
 // its butterfly inputs into registers, the warp syncs, then the outputs go back to the same buffer.
 template <int M, int R, bool FIRST>
-__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ tw, int pp, int tstep,
-                                         int lane) {
+__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ ptw, int pp, int lane) {
     constexpr int T = M / R;                 // butterflies in the pass
     constexpr int PER = (T + 31) / 32;       // per lane
     double2 u[PER][R];
@@ -70,11 +112,10 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
     for (int q = 0; q < PER; ++q) {
         const int i = lane + 32 * q;
         if (T >= 32 || i < T) {
-            const int k = i & (pp - 1);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                double2 v = x[i + r * T];
-                if (!FIRST && r > 0) v = cmul(v, tw[r * k * tstep]);
+                double2 v = x[pidx(i + r * T)];
+                if (!FIRST && r > 0) v = cmul(v, ptw[(q * (R - 1) + (r - 1)) * 32 + lane]);
                 u[q][r] = v;
             }
         }
@@ -92,13 +133,13 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
                 const double2 v2 = cadd(u[q][1], u[q][3]);
                 const double2 d = csub(u[q][1], u[q][3]);
                 const double2 v3 = make_double2(d.y, -d.x);          // -i * d
-                x[j] = cadd(v0, v2);
-                x[j + pp] = cadd(v1, v3);
-                x[j + 2 * pp] = csub(v0, v2);
-                x[j + 3 * pp] = csub(v1, v3);
+                x[pidx(j)] = cadd(v0, v2);
+                x[pidx(j + pp)] = cadd(v1, v3);
+                x[pidx(j + 2 * pp)] = csub(v0, v2);
+                x[pidx(j + 3 * pp)] = csub(v1, v3);
             } else {
-                x[j] = cadd(u[q][0], u[q][1]);
-                x[j + pp] = csub(u[q][0], u[q][1]);
+                x[pidx(j)] = cadd(u[q][0], u[q][1]);
+                x[pidx(j + pp)] = csub(u[q][0], u[q][1]);
             }
         }
     }
@@ -106,24 +147,19 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
 }
 
 // complex FFT of length M (power of two, 128/256/512) as radix-4 passes (+ one radix-2 pass for odd log2)
-template <int M, int NF>
-__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ tw, int lane) {
+template <int M>
+__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ ptw, int lane) {
+    using P = FftPlan<M>;
+    fft_pass<M, 4, true>(x, ptw, 1, lane);
+    fft_pass<M, 4, false>(x, ptw + P::offset(0) * 32, 4, lane);
+    fft_pass<M, 4, false>(x, ptw + P::offset(1) * 32, 16, lane);
     if (M == 256) {
-        fft_pass<M, 4, true>(x, tw, 1, NF / 4, lane);
-        fft_pass<M, 4, false>(x, tw, 4, NF / 16, lane);
-        fft_pass<M, 4, false>(x, tw, 16, NF / 64, lane);
-        fft_pass<M, 4, false>(x, tw, 64, NF / 256, lane);
+        fft_pass<M, 4, false>(x, ptw + P::offset(2) * 32, 64, lane);
     } else if (M == 128) {
-        fft_pass<M, 4, true>(x, tw, 1, NF / 4, lane);
-        fft_pass<M, 4, false>(x, tw, 4, NF / 16, lane);
-        fft_pass<M, 4, false>(x, tw, 16, NF / 64, lane);
-        fft_pass<M, 2, false>(x, tw, 64, NF / 128, lane);
+        fft_pass<M, 2, false>(x, ptw + P::offset(2) * 32, 64, lane);
     } else {
-        fft_pass<M, 4, true>(x, tw, 1, NF / 4, lane);
-        fft_pass<M, 4, false>(x, tw, 4, NF / 16, lane);
-        fft_pass<M, 4, false>(x, tw, 16, NF / 64, lane);
-        fft_pass<M, 4, false>(x, tw, 64, NF / 256, lane);
-        fft_pass<M, 2, false>(x, tw, 256, NF / 512, lane);
+        fft_pass<M, 4, false>(x, ptw + P::offset(2) * 32, 64, lane);
+        fft_pass<M, 2, false>(x, ptw + P::offset(3) * 32, 256, lane);
     }
 }
 
@@ -131,24 +167,37 @@ constexpr int kFrontWarps = 8;
 constexpr int kFramesPerWarp = 8;
 
 template <int NF>
-__global__ void __launch_bounds__(kFrontWarps * 32) fadb_frontend_kernel(const FrontParams p) {
-    constexpr int M = NF / 2;
-    constexpr int SPEC_PITCH = M + 4;        // floats per warp spectrum (M + 1 used)
-    extern __shared__ __align__(16) uint8_t fsm[];
-    double2* s_tw = reinterpret_cast<double2*>(fsm);                                  // [NF]
-    double* s_win = reinterpret_cast<double*>(fsm + NF * 16);                         // [NF] (zero beyond win_len)
-    double2* s_buf = reinterpret_cast<double2*>(fsm + NF * 16 + NF * 8);              // [warps][M]
-    float* s_spec = reinterpret_cast<float*>(fsm + NF * 16 + NF * 8 + kFrontWarps * M * 16);   // [warps][SPEC_PITCH]
+struct FrontSmem {
+    static constexpr int M = NF / 2;
+    static constexpr int kBufSlots = M + M / 8 + 2;                       // padded complex buffer per warp
+    static constexpr int kSpecPitch = M + 4;                              // floats per warp spectrum (M + 1 used)
+    static constexpr int kTwBytes = (M + 1) * 16;                         // split twiddles exp(-2 pi i k/NF), k = 0..M
+    static constexpr int kWinBytes = NF * 8;
+    static constexpr int kPtwBytes = FftPlan<M>::kSlots * 16;
+    static constexpr int kBufBytes = kFrontWarps * kBufSlots * 16;
+    static constexpr int kSpecBytes = kFrontWarps * kSpecPitch * 4;
+    static constexpr int kTotal = kTwBytes + kWinBytes + kPtwBytes + kBufBytes + kSpecBytes;
+};
 
-    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) {
-        s_tw[i] = p.tw[i];
-        s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
-    }
+template <int NF>
+__global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(const FrontParams p) {
+    using S = FrontSmem<NF>;
+    constexpr int M = NF / 2;
+    extern __shared__ __align__(16) uint8_t fsm[];
+    double2* s_tw = reinterpret_cast<double2*>(fsm);                                        // [M + 1]
+    double* s_win = reinterpret_cast<double*>(fsm + S::kTwBytes);                           // [NF] (zero beyond win_len)
+    double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);          // per-pass twiddles
+    double2* s_buf = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes);
+    float* s_spec = reinterpret_cast<float*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes + S::kBufBytes);
+
+    for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
+    build_pass_twiddles<M, NF>(s_ptw, p.tw);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2* x = s_buf + warp * M;
-    float* spec = s_spec + warp * SPEC_PITCH;
+    double2* x = s_buf + warp * S::kBufSlots;
+    float* spec = s_spec + warp * S::kSpecPitch;
     const int clip = blockIdx.y;
     const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
     float* out = p.out + (size_t)clip * p.rows_out * 64;
@@ -201,19 +250,20 @@ __global__ void __launch_bounds__(kFrontWarps * 32) fadb_frontend_kernel(const F
                     s1 = __fdiv_rn(truncf(__fmul_rn(s1, 32767.0f)), 32767.0f);
                 }
             }
-            x[n] = make_double2((double)s0 * s_win[2 * n], (double)s1 * s_win[2 * n + 1]);
+            const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * n]);
+            x[pidx(n)] = make_double2((double)s0 * wn.x, (double)s1 * wn.y);
         }
         __syncwarp();
 
-        fft_inplace<M, NF>(x, s_tw, lane);
+        fft_inplace<M>(x, s_ptw, lane);
 
         // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32
 #pragma unroll
         for (int q = 0; q <= M / 32; ++q) {
             const int k = lane + 32 * q;
             if (k <= M) {
-                const double2 a = x[k & (M - 1)];
-                const double2 bz = x[(M - k) & (M - 1)];
+                const double2 a = x[pidx(k & (M - 1))];
+                const double2 bz = x[pidx((M - k) & (M - 1))];
                 const double2 ze = make_double2(0.5 * (a.x + bz.x), 0.5 * (a.y - bz.y));
                 const double2 zo = make_double2(0.5 * (a.y + bz.y), -0.5 * (a.x - bz.x));   // (a - conj b) / (2i)
                 const double2 w = s_tw[k];                                                   // tw[M] = -1
@@ -337,9 +387,7 @@ static int build_tables(int model) {
 }
 
 template <int NF>
-static constexpr int front_smem() {
-    return NF * 16 + NF * 8 + kFrontWarps * (NF / 2) * 16 + kFrontWarps * (NF / 2 + 4) * 4;
-}
+static constexpr int front_smem() { return FrontSmem<NF>::kTotal; }
 
 int frontend_init(fadb_handle* h) {
     (void)h;

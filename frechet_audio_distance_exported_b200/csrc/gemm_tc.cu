@@ -46,6 +46,7 @@ struct GemmParams {
     int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
     int kb_begin, kb_end; // K-block range of this launch (whole K unless the exact-accumulation path splits it)
     int raw;              // 0 = fused epilogue; 1 = write raw fp32 partial sums; 2 = add them to out_f32
+    int resb;             // 1 = the whole B operand (all K blocks of the single N tile) stays resident in smem
     int relu;
     int pool;             // 0 none, 1 max, 2 avg
     int Ho, Wo;           // output spatial dims (after pooling)
@@ -68,7 +69,7 @@ struct GemmCfg {
     static constexpr int kMaxStages = 8;
     static constexpr int kTmemCols = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
     static constexpr int kExtraBytes = 256 /*barriers*/ + 1024 /*alignment slack*/;
-    static constexpr int kMaxSmemBytes = 4 * 49152 + kExtraBytes;     // 192 KB of stages at most
+    static constexpr int kMaxSmemBytes = 232448;                      // 227 KB: the per-CTA opt-in maximum
     static int stages_for(int budget_bytes) {
         int s = budget_bytes / kStageBytes;
         if (s > kMaxStages) s = kMaxStages;
@@ -212,12 +213,17 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     const uint32_t base = (raw_addr + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-B alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    // layout: [resident B: nkb x kBBytes (resb only)] [stages] [barriers]
+    const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * Cfg::kBBytes : 0;
+    const int stage_pitch = p.resb ? kABytes : Cfg::kStageBytes;
+    const uint32_t stage_base = base + res_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + res_bytes + kStages * stage_pitch);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages]
     const uint32_t bar_tfull = bar_empty + 8 * kStages;              // [2]
     const uint32_t bar_tempty = bar_tfull + 16;                      // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    const uint32_t bar_bres = bar_tempty + 16;                       // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             mbar_init(bar_tfull + 8 * s, 1);
             mbar_init(bar_tempty + 8 * s, 4);                        // one arrive per epilogue warp
         }
+        mbar_init(bar_bres, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
@@ -254,6 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if (p.resb && blockIdx.x < p.num_tiles) {
+                // weights of the (single) N tile: loaded once per CTA, reused by every tile
+                mbar_arrive_expect_tx(bar_bres, (uint32_t)res_bytes);
+                for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
+                    tma_load_2d(&p.tmB[0], bar_bres, base + (kbg - p.kb_begin) * Cfg::kBBytes, kbg * kBlockK, 0);
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int m = tile / p.tiles_n;
                 const int n0 = (tile - m * p.tiles_n) * BN;
@@ -271,11 +284,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     int dy = 0, dx = 0;
                     if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
-                    const uint32_t sa = base + stage * Cfg::kStageBytes;
-                    const uint32_t sb = sa + kABytes;
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+                    const uint32_t sa = stage_base + stage * stage_pitch;
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
                     tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                    tma_load_2d(tb, bar_full + 8 * stage, sb, kb * kBlockK, n0);
+                    if (!p.resb) tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -289,6 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            if (p.resb && blockIdx.x < p.num_tiles) {
+                mbar_wait(bar_bres, 0, p.err_flag);
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -298,9 +314,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // TMA bytes landed
                     tc_fence_after();
-                    const uint32_t sa = base + stage * Cfg::kStageBytes;
+                    const uint32_t sa = stage_base + stage * stage_pitch;
                     const uint64_t da = make_sw128_desc(sa);
-                    const uint64_t db = make_sw128_desc(sa + kABytes);
+                    const uint64_t db = make_sw128_desc(p.resb ? base + (kb - p.kb_begin) * Cfg::kBBytes : sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
@@ -666,16 +682,25 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     const int budget = h->gemm_smem_budget;
     auto launch = [&](const GemmParams& q) {
         GemmParams pp = q;
-        if (BN == 256) {
-            pp.stages = GemmCfg<256>::stages_for(budget);
-            fadb_gemm_tc_kernel<256><<<grid, kThreads, pp.stages * GemmCfg<256>::kStageBytes + GemmCfg<256>::kExtraBytes, st>>>(pp);
-        } else if (BN == 128) {
-            pp.stages = GemmCfg<128>::stages_for(budget);
-            fadb_gemm_tc_kernel<128><<<grid, kThreads, pp.stages * GemmCfg<128>::kStageBytes + GemmCfg<128>::kExtraBytes, st>>>(pp);
+        const int b_bytes = BN * kBlockK * 2;
+        // resident-B: short-K layers whose whole weight slab fits next to >= 4 A stages (VGGish conv2, CNN14
+        // block1.conv2): halves the L2 -> SM traffic of a layer that is L2-bandwidth bound, not MMA bound
+        const int res = (pp.kb_end - pp.kb_begin) * b_bytes;
+        pp.resb = (h->resident_b && npass == 1 && pp.tiles_n == 1 && res + 4 * kABytes <= budget) ? 1 : 0;
+        int smem;
+        if (pp.resb) {
+            pp.stages = (budget - res) / kABytes;
+            if (pp.stages > 8) pp.stages = 8;
+            smem = res + pp.stages * kABytes + GemmCfg<64>::kExtraBytes;
         } else {
-            pp.stages = GemmCfg<64>::stages_for(budget);
-            fadb_gemm_tc_kernel<64><<<grid, kThreads, pp.stages * GemmCfg<64>::kStageBytes + GemmCfg<64>::kExtraBytes, st>>>(pp);
+            pp.stages = budget / (kABytes + b_bytes);
+            if (pp.stages > 8) pp.stages = 8;
+            if (pp.stages < 2) pp.stages = 2;
+            smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes;
         }
+        if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, smem, st>>>(pp);
+        else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, smem, st>>>(pp);
+        else fadb_gemm_tc_kernel<64><<<grid, kThreads, smem, st>>>(pp);
         h->launches++;
     };
     const int nk = npass * io.taps * p.cin_blocks;
