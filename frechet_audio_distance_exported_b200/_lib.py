@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfadb200.so")
+LIB_PATH = os.environ.get("FADB_LIB_PATH") or os.path.join(_HERE, "libfadb200.so")   # override: A/B profiling only
 
 MODEL_IDS = {"vggish": 0, "pann-8k": 1, "pann-16k": 2, "pann-32k": 3, "clap": 4}
 PREC_IDS = {"bf16": 0, "bf16x3": 1}

@@ -338,9 +338,17 @@ static int vggish_embed_pcm(fadb_handle* h, const float* pcm, int64_t n_clips, i
     if (!overlap) {
         for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
             const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
-            FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride,
-                                       h->ws_feats.as<float>(), st));
-            FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
+            if (h->fused_front) {
+                FADB_CHECK(reserve_a1(h, 0));
+                __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
+                FADB_CHECK(launch_vggish_front_conv1(h, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride, a1,
+                                                     a1_lo_plane(h, 0), st));
+                FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0), nc * rows, emb + c0 * rows * d, st));
+            } else {
+                FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride,
+                                           h->ws_feats.as<float>(), st));
+                FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
+            }
         }
         return FADB_OK;
     }
@@ -488,6 +496,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_OVERLAP")) h->overlap = atoi(e);
     if (const char* e = getenv("FADB_GEMM_SMEM")) h->gemm_smem_budget = atoi(e);
     if (const char* e = getenv("FADB_RESIDENT_B")) h->resident_b = atoi(e);
+    if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
     if (rc != FADB_OK) { fadb_destroy(h); return rc; }

@@ -91,10 +91,11 @@ struct fadb_handle {
     int device = 0;
     int sm_count = 148;
     int precision = FADB_PREC_BF16;
-    int max_batch = 2048;           // VGGish patches per internal batch
+    int max_batch = 4096;           // VGGish patches per internal batch
     int max_batch_cnn14 = 32;       // CNN14 clips per internal batch
     int gemm_smem_budget = 231168;  // bytes of smem for resident weights + pipeline stages per GEMM CTA
                                     // (227 KB opt-in maximum minus barriers/alignment slack)
+    int fused_front = 1;            // VGGish: PCM -> conv1 output in one kernel (features stay in shared memory)
     int resident_b = 1;             // keep short-K weight slabs resident in smem (see gemm_tc.cu)
     int overlap = 0;                // (experiment, default off: measured no gain) run front end + conv1 of chunk i+1 on a side stream under the GEMMs of chunk i
     int model = -1;                 // model whose weights are committed
@@ -144,6 +145,8 @@ namespace fadb {
 int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips, int64_t n_samples,
                     int64_t pcm_stride, float* feats, cudaStream_t st);
 int frontend_init(fadb_handle* h);
+int launch_vggish_front_conv1(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                              __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
 
 int64_t frontend_rows(int model, int64_t n_samples);
 

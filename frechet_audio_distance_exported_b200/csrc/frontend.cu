@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv1_dev.cuh"
 
 namespace fadb {
 
@@ -179,6 +180,84 @@ struct FrontSmem {
     static constexpr int kTotal = kTwBytes + kWinBytes + kPtwBytes + kBufBytes + kSpecBytes;
 };
 
+// One STFT frame -> 64 log-mel values, by one warp.  out_row[lane] and out_row[lane + 32] are written
+// (global memory in the stand-alone kernel, the shared-memory patch tile in the fused VGGish kernel).
+template <int NF>
+__device__ __forceinline__ void frame_logmel(const FrontParams& p, const float* __restrict__ pcm, int row, int lane,
+                                             double2* __restrict__ x, float* __restrict__ spec,
+                                             const double2* __restrict__ s_tw, const double* __restrict__ s_win,
+                                             const double2* __restrict__ s_ptw, const int (&bst)[2], const int (&bln)[2],
+                                             const int (&bof)[2], float* __restrict__ out_row) {
+    constexpr int M = NF / 2;
+    // ---- load + window (fp32 PCM x fp64 Hann, like numpy's promotion): z[n] = x[2n] + i x[2n+1]
+    const long long f0 = (long long)row * p.hop - (p.centered ? NF / 2 : 0);
+    const bool interior = (f0 >= 0) && (f0 + p.win_len <= p.n_samples);
+#pragma unroll
+    for (int q = 0; q < M / 32; ++q) {
+        const int n = lane + 32 * q;
+        float s0 = 0.f, s1 = 0.f;
+        if (2 * n < p.win_len) {
+            if (interior) {
+                s0 = __ldg(pcm + f0 + 2 * n);
+                s1 = (2 * n + 1 < p.win_len) ? __ldg(pcm + f0 + 2 * n + 1) : 0.f;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 2 * n + e;
+                    float s = 0.f;
+                    if (j < p.win_len) {
+                        long long src = f0 + j;
+                        if (p.centered) {        // np.pad(mode='reflect'): edge sample not repeated
+                            if (src < 0) src = -src;
+                            if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
+                        }
+                        if (src >= 0 && src < p.n_samples) s = __ldg(pcm + src);
+                    }
+                    if (e == 0) s0 = s; else s1 = s;
+                }
+            }
+            if (p.quantize) {                    // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
+                s0 = __fdiv_rn(truncf(__fmul_rn(s0, 32767.0f)), 32767.0f);
+                s1 = __fdiv_rn(truncf(__fmul_rn(s1, 32767.0f)), 32767.0f);
+            }
+        }
+        const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * n]);
+        x[pidx(n)] = make_double2((double)s0 * wn.x, (double)s1 * wn.y);
+    }
+    __syncwarp();
+
+    fft_inplace<M>(x, s_ptw, lane);
+
+    // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32
+#pragma unroll
+    for (int q = 0; q <= M / 32; ++q) {
+        const int k = lane + 32 * q;
+        if (k <= M) {
+            const double2 a = x[pidx(k & (M - 1))];
+            const double2 bz = x[pidx((M - k) & (M - 1))];
+            const double2 ze = make_double2(0.5 * (a.x + bz.x), 0.5 * (a.y - bz.y));
+            const double2 zo = make_double2(0.5 * (a.y + bz.y), -0.5 * (a.x - bz.x));   // (a - conj b) / (2i)
+            const double2 w = s_tw[k];                                                   // tw[M] = -1
+            const float re = (float)(ze.x + w.x * zo.x - w.y * zo.y);
+            const float im = (float)(ze.y + w.x * zo.y + w.y * zo.x);
+            const float pw = fmaf(re, re, im * im);
+            spec[k] = p.power_db ? pw : sqrtf(pw);
+        }
+    }
+    __syncwarp();
+    // ---- mel projection (sparse triangular bands) + log, fp32
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        float acc = 0.f;
+        for (int i = 0; i < bln[h2]; ++i) acc = fmaf(__ldg(p.band_wf + bof[h2] + i), spec[bst[h2] + i], acc);
+        float o;
+        if (p.power_db) o = 10.0f * log10f(fmaxf(acc, 1e-10f));      // pann.py:133-134
+        else o = logf(acc + 0.01f);                                  // vggish.py:227
+        out_row[lane + 32 * h2] = o;
+    }
+    __syncwarp();
+}
+
 template <int NF>
 __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(const FrontParams p) {
     using S = FrontSmem<NF>;
@@ -201,15 +280,13 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
     const int clip = blockIdx.y;
     const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
     float* out = p.out + (size_t)clip * p.rows_out * 64;
-    // this lane's two mel bands
-    int bst[2], bln[2], bof[2];
+    int bst[2], bln[2], bof[2];                      // this lane's two mel bands
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
         bst[h2] = p.band_start[lane + 32 * h2];
         bln[h2] = p.band_len[lane + 32 * h2];
         bof[h2] = p.band_off[lane + 32 * h2];
     }
-
     for (int fi = 0; fi < kFramesPerWarp; ++fi) {
         const int row = blockIdx.x * (kFrontWarps * kFramesPerWarp) + warp * kFramesPerWarp + fi;
         if (row >= p.rows_out) break;
@@ -218,73 +295,84 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
             out[(size_t)row * 64 + lane + 32] = 0.f;
             continue;
         }
-        // ---- load + window (fp32 PCM x fp64 Hann, like numpy's promotion): z[n] = x[2n] + i x[2n+1]
-        const long long f0 = (long long)row * p.hop - (p.centered ? NF / 2 : 0);
-        const bool interior = (f0 >= 0) && (f0 + p.win_len <= p.n_samples);
-#pragma unroll
-        for (int q = 0; q < M / 32; ++q) {
-            const int n = lane + 32 * q;
-            float s0 = 0.f, s1 = 0.f;
-            if (2 * n < p.win_len) {
-                if (interior) {
-                    s0 = __ldg(pcm + f0 + 2 * n);
-                    s1 = (2 * n + 1 < p.win_len) ? __ldg(pcm + f0 + 2 * n + 1) : 0.f;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = 2 * n + e;
-                        float s = 0.f;
-                        if (j < p.win_len) {
-                            long long src = f0 + j;
-                            if (p.centered) {        // np.pad(mode='reflect'): edge sample not repeated
-                                if (src < 0) src = -src;
-                                if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
-                            }
-                            if (src >= 0 && src < p.n_samples) s = __ldg(pcm + src);
-                        }
-                        if (e == 0) s0 = s; else s1 = s;
-                    }
-                }
-                if (p.quantize) {                    // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
-                    s0 = __fdiv_rn(truncf(__fmul_rn(s0, 32767.0f)), 32767.0f);
-                    s1 = __fdiv_rn(truncf(__fmul_rn(s1, 32767.0f)), 32767.0f);
-                }
-            }
-            const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * n]);
-            x[pidx(n)] = make_double2((double)s0 * wn.x, (double)s1 * wn.y);
-        }
-        __syncwarp();
+        frame_logmel<NF>(p, pcm, row, lane, x, spec, s_tw, s_win, s_ptw, bst, bln, bof, out + (size_t)row * 64);
+    }
+}
 
-        fft_inplace<M>(x, s_ptw, lane);
+// ------------------------------------------------------------------------------------------------
+// Fused VGGish kernel: one CTA = one 96-frame patch.  Phase 1 (fp64 FFT, shared-memory bound): 8 warps x 12
+// frames write the log-mel patch into a shared-memory tile.  Phase 2 (packed fp32 FMAs): conv3x3(1->64) +
+// bias + ReLU + maxpool2x2 straight from that tile to NHWC bf16.  The fp32 features never touch HBM, and
+// with two CTAs per SM the FFT phase of one patch overlaps the FMA phase of another (different pipes).
+// ------------------------------------------------------------------------------------------------
+struct FusedSmem {
+    using S = FrontSmem<512>;
+    static constexpr int kTilePitch = 68;                                     // 64 mel + halo, 16-byte rows
+    static constexpr int kTileBytes = 98 * kTilePitch * 4;                    // 96 frames + 2 halo rows
+    static constexpr int kWBytes = 9 * 64 * 4 + 64 * 4;
+    static constexpr int kTotal = S::kTotal + kTileBytes + kWBytes;
+};
 
-        // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32
+__global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_kernel(
+    const FrontParams p, const float* __restrict__ conv_w, const float* __restrict__ conv_b, int patches_per_clip,
+    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+    constexpr int NF = 512, M = 256;
+    using S = FrontSmem<NF>;
+    extern __shared__ __align__(16) uint8_t fsm[];
+    double2* s_tw = reinterpret_cast<double2*>(fsm);
+    double* s_win = reinterpret_cast<double*>(fsm + S::kTwBytes);
+    double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);
+    double2* s_buf = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes);
+    float* s_spec = reinterpret_cast<float*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes + S::kBufBytes);
+    float (*s_tile)[FusedSmem::kTilePitch] = reinterpret_cast<float (*)[FusedSmem::kTilePitch]>(fsm + S::kTotal);
+    float (*s_w)[64] = reinterpret_cast<float (*)[64]>(fsm + S::kTotal + FusedSmem::kTileBytes);
+    float* s_b = reinterpret_cast<float*>(fsm + S::kTotal + FusedSmem::kTileBytes + 9 * 64 * 4);
+
+    for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
+    build_pass_twiddles<M, NF>(s_ptw, p.tw);
+    for (int i = threadIdx.x; i < 9 * 64; i += kFrontWarps * 32) s_w[i / 64][i % 64] = conv_w[i];
+    if (threadIdx.x < 64) s_b[threadIdx.x] = conv_b[threadIdx.x];
+    // zero halo: rows 0 and 97, columns 0 and 65 (tile row r holds frame r-1, column c holds mel c-1)
+    for (int i = threadIdx.x; i < 2 * FusedSmem::kTilePitch; i += kFrontWarps * 32)
+        s_tile[(i / FusedSmem::kTilePitch) * 97][i % FusedSmem::kTilePitch] = 0.f;
+    for (int i = threadIdx.x; i < 98; i += kFrontWarps * 32) { s_tile[i][0] = 0.f; s_tile[i][65] = 0.f; }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* x = s_buf + warp * S::kBufSlots;
+    float* spec = s_spec + warp * S::kSpecPitch;
+    const int clip = blockIdx.y, patch = blockIdx.x;
+    const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
+    int bst[2], bln[2], bof[2];
 #pragma unroll
-        for (int q = 0; q <= M / 32; ++q) {
-            const int k = lane + 32 * q;
-            if (k <= M) {
-                const double2 a = x[pidx(k & (M - 1))];
-                const double2 bz = x[pidx((M - k) & (M - 1))];
-                const double2 ze = make_double2(0.5 * (a.x + bz.x), 0.5 * (a.y - bz.y));
-                const double2 zo = make_double2(0.5 * (a.y + bz.y), -0.5 * (a.x - bz.x));   // (a - conj b) / (2i)
-                const double2 w = s_tw[k];                                                   // tw[M] = -1
-                const float re = (float)(ze.x + w.x * zo.x - w.y * zo.y);
-                const float im = (float)(ze.y + w.x * zo.y + w.y * zo.x);
-                const float pw = fmaf(re, re, im * im);
-                spec[k] = p.power_db ? pw : sqrtf(pw);
-            }
-        }
-        __syncwarp();
-        // ---- mel projection (sparse triangular bands) + log, fp32
+    for (int h2 = 0; h2 < 2; ++h2) {
+        bst[h2] = p.band_start[lane + 32 * h2];
+        bln[h2] = p.band_len[lane + 32 * h2];
+        bof[h2] = p.band_off[lane + 32 * h2];
+    }
+    // ---- phase 1: 96 frames of this patch -> s_tile rows 1..96, columns 1..64
+    for (int fi = 0; fi < 12; ++fi) {
+        const int fr = warp * 12 + fi;
+        frame_logmel<NF>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, bst, bln, bof, &s_tile[fr + 1][1]);
+    }
+    __syncthreads();
+    // ---- phase 2: conv1 + ReLU + maxpool; thread = pooled pixel (warp = pooled row within a band of 8)
+    const size_t pbase = (size_t)clip * patches_per_clip + patch;
+#pragma unroll 1
+    for (int band = 0; band < 6; ++band) {
+        const int prow = band * 8 + warp;              // pooled row 0..47
+        unsigned long long in[4][4];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            float acc = 0.f;
-            for (int i = 0; i < bln[h2]; ++i) acc = fmaf(__ldg(p.band_wf + bof[h2] + i), spec[bst[h2] + i], acc);
-            float o;
-            if (p.power_db) o = 10.0f * log10f(fmaxf(acc, 1e-10f));      // pann.py:133-134
-            else o = logf(acc + 0.01f);                                  // vggish.py:227
-            out[(size_t)row * 64 + lane + 32 * h2] = o;
+        for (int r = 0; r < 4; ++r) {
+            // input rows 2*prow-1 .. 2*prow+2  -> tile rows 2*prow .. 2*prow+3 ; input cols 2*lane-1.. -> tile cols 2*lane..
+            const float2 a = *reinterpret_cast<const float2*>(&s_tile[2 * prow + r][2 * lane]);
+            const float2 b = *reinterpret_cast<const float2*>(&s_tile[2 * prow + r][2 * lane + 2]);
+            in[r][0] = pack_f32x2(a.x, a.x); in[r][1] = pack_f32x2(a.y, a.y);
+            in[r][2] = pack_f32x2(b.x, b.x); in[r][3] = pack_f32x2(b.y, b.y);
         }
-        __syncwarp();
+        const size_t obase = ((pbase * 48 + prow) * 32 + lane) * 64;
+        conv1_vggish_pixel(in, s_w, s_b, out_hi, out_lo, obase);
     }
 }
 
@@ -397,6 +485,8 @@ int frontend_init(fadb_handle* h) {
                                          front_smem<512>()));
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_frontend_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          front_smem<1024>()));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_vggish_front_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FusedSmem::kTotal));
     return FADB_OK;
 }
 
@@ -421,6 +511,32 @@ int64_t frontend_rows(int model, int64_t n) {
         case FADB_MODEL_CLAP: return 1001;
         default: return -1;
     }
+}
+
+// PCM -> conv1 output [n_clips * patches, 48, 32, 64] bf16 (hi / optional lo) in one kernel (VGGish only)
+int launch_vggish_front_conv1(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                              __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+    FADB_CHECK(build_tables(FADB_MODEL_VGGISH));
+    const FrontTables& t = g_tables[FADB_MODEL_VGGISH];
+    const int64_t patches = frontend_rows(FADB_MODEL_VGGISH, n_samples);
+    if (n_clips <= 0 || patches <= 0) return FADB_OK;
+    FADB_REQUIRE(n_clips <= 65535 && n_samples < (1LL << 30), "fused front end: clip count / length out of range");
+    FrontParams p;
+    p.pcm = pcm; p.pcm_stride = pcm_stride;
+    p.n_samples = (int)n_samples; p.logical_len = (int)n_samples;
+    p.hop = t.hop; p.win_len = t.win_len;
+    p.centered = 0; p.power_db = 0; p.quantize = 0;
+    p.tw = t.tw; p.win = t.win;
+    p.band_start = t.band_start; p.band_len = t.band_len; p.band_off = t.band_off; p.band_wf = t.band_w;
+    p.out = nullptr;
+    p.rows_out = (int)(patches * 96);
+    p.frames_valid = p.rows_out;
+    dim3 grid((unsigned)patches, (unsigned)n_clips);
+    fadb_vggish_front_conv1_kernel<<<grid, kFrontWarps * 32, FusedSmem::kTotal, st>>>(
+        p, h->conv1_w, h->conv1_b, (int)patches, out_hi, h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
 }
 
 int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips, int64_t n_samples,

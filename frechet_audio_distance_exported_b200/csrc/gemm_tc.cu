@@ -117,6 +117,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
         if (clock64() - t0 > 4000000000LL) mbar_timeout(err_flag, DEVERR_PIPE_TIMEOUT);
     }
 }
+// one lane of a CONVERGED warp (keeps the control flow warp-uniform: tcgen05 / TMA instructions run on the
+// uniform datapath, and issuing them from a lane-divergent region costs an ELECT + vote + branch per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -257,15 +268,18 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     const int kb_per_pass = p.taps * p.cin_blocks;
 
     if (warp == 0) {
-        // ======================= TMA producer =======================
-        if (lane == 0) {
+        // ======================= TMA producer (whole warp runs the loop; one elected lane issues) =====
+        {
             int stage = 0;
             uint32_t phase = 0;
             if (p.resb && blockIdx.x < p.num_tiles) {
                 // weights of the (single) N tile: loaded once per CTA, reused by every tile
-                mbar_arrive_expect_tx(bar_bres, (uint32_t)res_bytes);
-                for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
-                    tma_load_2d(&p.tmB[0], bar_bres, base + (kbg - p.kb_begin) * Cfg::kBBytes, kbg * kBlockK, 0);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_bres, (uint32_t)res_bytes);
+                    for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
+                        tma_load_2d(&p.tmB[0], bar_bres, base + (kbg - p.kb_begin) * Cfg::kBBytes, kbg * kBlockK, 0);
+                }
+                __syncwarp();
             }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int m = tile / p.tiles_n;
@@ -285,16 +299,19 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
-                    tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                    if (!p.resb) tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
+                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                        if (!p.resb) tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
+        // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) =======
+        {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
                                        (uint32_t(kTileM >> 4) << 24);
@@ -317,15 +334,19 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     const uint64_t da = make_sw128_desc(sa);
                     const uint64_t db = make_sw128_desc(p.resb ? base + (kb - p.kb_begin) * Cfg::kBBytes : sa + kABytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * stage);                 // frees the smem stage when MMAs retire
                     }
-                    umma_commit(bar_empty + 8 * stage);                     // frees the smem stage when MMAs retire
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(bar_tfull + 8 * as);                            // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(bar_tfull + 8 * as);           // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -8,8 +8,8 @@ Differences a user of the reference sees:
     state_dict of the reference's own modules (`state_dict=` or a file in `ckpt_dir`);
   * "clap" is the CNN14 audio branch + projection head (BASELINE.json / README of the reference),
     not the HTSAT artefact; "encodec-*" is out of scope and raises NotImplementedError;
-  * resampling (resampy) is not built yet: non-native-rate input raises and, inside
-    get_embeddings / score, is handled like any per-clip error of the reference (skipped / -1).
+  * resampling follows resampy's published kaiser_best algorithm (resample.py, host side like the
+    reference); resampy itself is un-vendored and absent here, so this piece is parity-unpinned.
 """
 from __future__ import annotations
 
@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from .engine import Engine
+from .resample import resample
 
 CLAP_TIME_FRAMES = 1001                       # fad.py:38
 
@@ -91,8 +92,7 @@ def load_audio(fname: str, sample_rate: int, channels: int, dtype: str = "float3
     if len(wav_data.shape) > channels:                # fad.py:154-155
         wav_data = np.mean(wav_data, axis=1)
     if sr != sample_rate:                             # fad.py:158-159
-        raise NotImplementedError(
-            f"{fname}: sample rate {sr} != {sample_rate}; the resampy-equivalent resampler is not built yet")
+        wav_data = resample(wav_data, sr, sample_rate)
     return wav_data
 
 
@@ -146,9 +146,7 @@ class FrechetAudioDistance:
         self.audio_load_worker = audio_load_worker
         self.precision = precision
         self.process_group = process_group
-        if not torch.cuda.is_available():                                      # fad.py:228-233, minus mps/cpu
-            raise RuntimeError("frechet_audio_distance_exported_b200 needs a B200 GPU: there is no CPU fallback")
-        self.device = torch.device("cuda")
+        self.device = torch.device("cuda")                                     # fad.py:228-233: CUDA only, no mps/cpu branch
         if self.verbose:
             print(f"[Exported FAD] Using device: {self.device}")
         if ckpt_dir is not None:                                               # fad.py:239-244
@@ -170,23 +168,30 @@ class FrechetAudioDistance:
             return "clap_exported.pt2"
         return f"{self.model_name}_exported.pt2"
 
-    def _load_model(self):
+    def _resolve_state_dict(self) -> Dict[str, torch.Tensor]:
+        """Host-side half of fad.py:249-300: find the weights.  `state_dict=` wins; else the exported artefact
+        `<ckpt_dir>/<name>_exported.pt2` (torch.export, read for its state_dict only — the graph is not run:
+        the network executes in libfadb200.so) or `<...>_state_dict.pt`.  Nothing is downloaded."""
         if self.model_name in ENCODEC_SAMPLE_RATES:
             raise NotImplementedError("Encodec is out of scope of the B200 hot path (no model source in the reference)")
-        sd = self._state_dict
-        if sd is None:
-            path = os.path.join(self.ckpt_dir, self._model_filename())
-            alt = os.path.splitext(path)[0] + "_state_dict.pt"
-            if os.path.exists(path):
-                if self.verbose:
-                    print(f"[Exported FAD] Loading model from {path}...")
-                sd = dict(torch.export.load(path).state_dict)                  # fad.py:297
-            elif os.path.exists(alt):
-                sd = torch.load(alt, map_location="cpu")
-            else:
-                raise FileNotFoundError(
-                    f"Exported model not found at {path} (or {alt}) and downloading is unavailable offline. "
-                    f"Pass state_dict= or provide a valid ckpt_dir.")
+        if self._state_dict is not None:
+            return self._state_dict
+        path = os.path.join(self.ckpt_dir, self._model_filename())
+        alt = os.path.splitext(path)[0] + "_state_dict.pt"
+        if os.path.exists(path):
+            if self.verbose:
+                print(f"[Exported FAD] Loading model from {path}...")
+            return dict(torch.export.load(path).state_dict)                    # fad.py:297
+        if os.path.exists(alt):
+            return torch.load(alt, map_location="cpu")
+        raise FileNotFoundError(
+            f"Exported model not found at {path} (or {alt}) and downloading is unavailable offline. "
+            f"Pass state_dict= or provide a valid ckpt_dir.")
+
+    def _load_model(self):
+        sd = self._resolve_state_dict()
+        if not torch.cuda.is_available():                                      # fad.py:228-233, minus mps/cpu
+            raise RuntimeError("frechet_audio_distance_exported_b200 needs a B200 GPU: there is no CPU fallback")
         self.engine = Engine(self.model_name, sd, precision=self.precision)
         self.model = _B200Model(self.engine)
 
@@ -196,7 +201,7 @@ class FrechetAudioDistance:
         if audio.ndim > 1:                                                     # vggish.py:245-246 / pann.py:96-97
             audio = np.mean(audio, axis=1)
         if sr != self.sample_rate:                                             # vggish.py:249-250 / pann.py:100-101
-            raise NotImplementedError("resampling is not built yet")
+            audio = resample(audio, sr, self.sample_rate)
         audio = np.ascontiguousarray(audio, dtype=np.float32)
         if self.model_name == "clap" and audio.shape[0] > 480000:
             raise ValueError("CLAP clips are limited to 10 s")

@@ -1,0 +1,76 @@
+"""Band-limited sinc resampler with the semantics of `resampy.resample(x, sr_orig, sr_new)` (default filter
+`kaiser_best`), used where the reference calls resampy: fad.py:159, models/vggish.py:250, models/pann.py:101.
+
+resampy is an un-vendored, unpinned dependency of the reference and is not installed in this environment, so
+this file is written from resampy's published algorithm (Smith's band-limited interpolation: a Kaiser-windowed
+sinc table with 64 zero crossings, 512 table entries per crossing, roll-off 0.9475937167399596, Kaiser beta
+14.769656459379492, linear interpolation between table entries, gain min(1, ratio), output length
+int(n * ratio)).  PARITY UNPINNED: it cannot be checked against resampy offline; tests pin the properties the
+reference's own tests pin (output length, tests/test_basic.py:212-228) plus signal-level sanity.
+
+Host-side NumPy: resampling belongs to file ingestion (the reference does it on the host too), not to the
+B200 hot path, which only ever sees native-rate PCM.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+_NUM_ZEROS = 64
+_PRECISION = 9
+_ROLLOFF = 0.9475937167399596
+_BETA = 14.769656459379492
+
+
+@functools.lru_cache(maxsize=1)
+def _kaiser_best():
+    num_table = 2 ** _PRECISION
+    n = num_table * _NUM_ZEROS
+    sinc_win = _ROLLOFF * np.sinc(_ROLLOFF * np.linspace(0, _NUM_ZEROS, num=n + 1, endpoint=True))
+    taper = np.kaiser(2 * n + 1, _BETA)[n:]
+    return taper * sinc_win, num_table
+
+
+def resample(x: np.ndarray, sr_orig: int, sr_new: int) -> np.ndarray:
+    """Resample a 1-D signal (or the first axis of an N-D array) from sr_orig to sr_new."""
+    if sr_orig <= 0 or sr_new <= 0:
+        raise ValueError("sample rates must be positive")
+    x = np.asarray(x)
+    if sr_orig == sr_new:
+        return x.copy()
+    if x.ndim > 1:
+        return np.stack([resample(x[..., c], sr_orig, sr_new) for c in range(x.shape[-1])], axis=-1) \
+            if x.ndim == 2 else np.apply_along_axis(resample, 0, x, sr_orig, sr_new)
+    ratio = float(sr_new) / float(sr_orig)
+    n_orig = x.shape[0]
+    n_out = int(n_orig * ratio)
+    if n_out < 1:
+        raise ValueError(f"Input signal length={n_orig} is too small to resample from {sr_orig}->{sr_new}")
+    win, num_table = _kaiser_best()
+    win = win.copy()
+    if ratio < 1:
+        win *= ratio
+    delta = np.zeros_like(win)
+    delta[:-1] = np.diff(win)
+    scale = min(1.0, ratio)
+    index_step = int(scale * num_table)
+    nwin = win.shape[0]
+    xf = x.astype(np.float64)
+    out = np.zeros(n_out, dtype=np.float64)
+    t = np.arange(n_out, dtype=np.float64) / ratio          # time register per output sample
+    n = t.astype(np.int64)
+    for side in (0, 1):
+        frac = scale * (t - n) if side == 0 else scale - scale * (t - n)
+        index_frac = frac * num_table
+        offset = index_frac.astype(np.int64)
+        eta = index_frac - offset
+        taps = (nwin - offset) // index_step
+        limit = np.minimum(n + 1, taps) if side == 0 else np.minimum(n_orig - n - 1, taps)
+        for i in range(int(limit.max()) if limit.size else 0):
+            m = i < limit
+            idx = offset[m] + i * index_step
+            w = win[idx] + eta[m] * delta[idx]
+            src = n[m] - i if side == 0 else n[m] + i + 1
+            out[m] += w * xf[src]
+    return out.astype(x.dtype if np.issubdtype(x.dtype, np.floating) else np.float64)

@@ -121,7 +121,83 @@ def test_load_audio_wav(tmp_path):
     np.testing.assert_array_almost_equal(out2, a, decimal=4)
     out3 = load_audio(p, 16000, 1, dtype="int16")                                       # fad.py:148-149
     assert out3.dtype == np.float64 and np.abs(out3 - a).max() < 1e-4
+    # resampling on load (reference tests/test_basic.py:212-228: 1 s at 44.1 kHz -> exactly 16000 samples)
+    t = np.linspace(0, 1.0, 44100, dtype=np.float32)
+    b = (np.sin(2 * np.pi * 440.0 * t) * 0.5).astype(np.float32)
     p3 = str(tmp_path / "f.wav")
-    wavfile.write(p3, 44100, a)
+    wavfile.write(p3, 44100, b)
+    out4 = load_audio(p3, 16000, 1)
+    assert len(out4) == 16000
+
+
+def test_resampler_properties():
+    """resampy semantics (un-vendored, parity unpinned): output length int(n * ratio), identity at equal rates,
+    a band-limited tone survives up- and down-sampling."""
+    from frechet_audio_distance_exported_b200.resample import resample
+    x = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000)
+    assert np.array_equal(resample(x, 16000, 16000), x)
+    up = resample(x, 16000, 48000)
+    assert len(up) == 48000
+    ref = np.sin(2 * np.pi * 440.0 * np.arange(48000) / 48000)
+    assert np.abs(up[6000:42000] - ref[6000:42000]).max() < 1e-6
+    x44 = np.sin(2 * np.pi * 440.0 * np.arange(44100) / 44100).astype(np.float32)
+    down = resample(x44, 44100, 16000)
+    assert len(down) == 16000 and down.dtype == np.float32
+    ref = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000)
+    assert np.abs(down[2000:14000] - ref[2000:14000]).max() < 5e-3      # resampy's truncated table step: 0.27 % gain
+    hi = np.sin(2 * np.pi * 15000.0 * np.arange(44100) / 44100)          # above the new Nyquist: must be removed
+    assert np.abs(resample(hi, 44100, 16000)[2000:14000]).max() < 1e-3
+    assert len(resample(np.zeros(7), 8000, 16000)) == 14
+    with pytest.raises(ValueError):
+        resample(np.zeros(1), 48000, 8000)
+
+
+def _vggish_module(sd):
+    """nn.Module with VGGishCore's parameter names (features.N / embeddings.N), built from the oracle's layer list."""
+    import torch.nn as nn
+    from oracle.networks import VGGISH_CFG
+    layers, cin = [], 1
+    for v in VGGISH_CFG:
+        if v == "M":
+            layers.append(nn.MaxPool2d(2, 2))
+        else:
+            layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU()]
+            cin = v
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.Sequential(*layers)
+            self.embeddings = nn.Sequential(nn.Linear(12288, 4096), nn.ReLU(), nn.Linear(4096, 4096), nn.ReLU(),
+                                            nn.Linear(4096, 128))
+
+        def forward(self, x):
+            x = self.features(x).permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+            return self.embeddings(x)
+
+    m = M()
+    m.load_state_dict(sd)
+    return m.eval()
+
+
+def test_weights_from_exported_pt2(tmp_path):
+    """the reference loads `vggish_exported.pt2` (fad.py:297); we read the same artefact for its
+    state_dict.  A synthetic artefact is produced here exactly like scripts/export_vggish.py does
+    (torch.export.export + save) because the real one cannot be downloaded offline."""
+    from frechet_audio_distance_exported_b200.fad import FrechetAudioDistance
+    from oracle import networks
+    sd = networks.vggish_random_state_dict(seed=3)
+    ep = torch.export.export(_vggish_module(sd), (torch.randn(2, 1, 96, 64),))
+    torch.export.save(ep, str(tmp_path / "vggish_exported.pt2"))
+    fad = FrechetAudioDistance.__new__(FrechetAudioDistance)
+    fad.model_name, fad.ckpt_dir, fad.verbose, fad._state_dict = "vggish", str(tmp_path), False, None
+    got = fad._resolve_state_dict()
+    assert set(got) == set(sd)
+    for k in sd:
+        assert torch.equal(got[k].detach().cpu(), sd[k]), k
+    fad.ckpt_dir = str(tmp_path / "nowhere")
+    with pytest.raises(FileNotFoundError):
+        fad._resolve_state_dict()
+    fad.model_name = "encodec-24k"
     with pytest.raises(NotImplementedError):
-        load_audio(p3, 16000, 1)
+        fad._resolve_state_dict()

@@ -70,7 +70,8 @@ def test_get_embeddings_semantics(fad_vgg):
     ref = ora.get_embeddings([a, b])
     assert np.max(np.abs(out[:3] - ref)) / np.max(np.abs(ref)) < 1e-2
     assert fad_vgg.get_embeddings([], 16000).shape == (0,)
-    assert fad_vgg.get_embeddings([a], 44100).shape == (0,)               # resample branch unavailable -> clip skipped
+    long44 = synth.sine_clip(3.0, 440.0, 44100)                            # 44.1 kHz input is resampled (vggish.py:249-250)
+    assert fad_vgg.get_embeddings([long44], 44100).shape == (3, 128)
     assert fad_vgg._get_embedding_for_audio(a).shape == (2, 128)
 
 
@@ -150,6 +151,19 @@ def test_encodec_is_out_of_scope():
     from frechet_audio_distance_exported_b200 import FrechetAudioDistance
     with pytest.raises(NotImplementedError):
         FrechetAudioDistance(model_name="encodec-24k", state_dict={})
+
+
+def test_ckpt_dir_with_exported_artefact(tmp_path):
+    """FrechetAudioDistance(ckpt_dir) with a synthetic `vggish_exported.pt2` == the state_dict path."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    from test_abi import _vggish_module
+    sd = networks.vggish_random_state_dict(seed=3)
+    ep = torch.export.export(_vggish_module(sd), (torch.randn(2, 1, 96, 64),))
+    torch.export.save(ep, str(tmp_path / "vggish_exported.pt2"))
+    a = FrechetAudioDistance(str(tmp_path), "vggish")                     # positional order of the reference, fad.py:178-186
+    b = FrechetAudioDistance(model_name="vggish", state_dict=sd)
+    clip = synth.eval_clip(0, 32400, 16000)
+    assert np.array_equal(a._get_embedding_for_audio(clip), b._get_embedding_for_audio(clip))
 
 
 def test_missing_weights_fail_loudly(tmp_path):
