@@ -96,6 +96,7 @@ struct fadb_handle {
     int gemm_smem_budget = 231168;  // bytes of smem for resident weights + pipeline stages per GEMM CTA
                                     // (227 KB opt-in maximum minus barriers/alignment slack)
     int fused_front = 1;            // VGGish: PCM -> conv1 output in one kernel (features stay in shared memory)
+    int halo = 1;                   // 3x3 layers on large maps: one halo tile per channel block feeds all 9 taps
     int resident_b = 1;             // keep short-K weight slabs resident in smem (see gemm_tc.cu)
     int overlap = 0;                // (experiment, default off: measured no gain) run front end + conv1 of chunk i+1 on a side stream under the GEMMs of chunk i
     int model = -1;                 // model whose weights are committed

@@ -330,7 +330,22 @@ __global__ void __launch_bounds__(512) tridiag_step_kernel(double* __restrict__ 
         double* Arow = A + (size_t)row * d;
         const double vrow = sv[row], wrow = sw[row];
         double dot = 0.0;
-        for (int c = first + lane; c < d; c += 32) {
+        // 4 independent 256-byte row segments in flight per warp: all loads are issued before the first
+        // store (the one-element-per-iteration form serialised on the L2 round trip of every segment)
+        int c = first + lane;
+        for (; c + 96 < d; c += 128) {
+            const double a0 = Arow[c], a1 = Arow[c + 32], a2 = Arow[c + 64], a3 = Arow[c + 96];
+            const double b0 = fma(-vrow, sw[c], fma(-wrow, sv[c], a0));
+            const double b1 = fma(-vrow, sw[c + 32], fma(-wrow, sv[c + 32], a1));
+            const double b2 = fma(-vrow, sw[c + 64], fma(-wrow, sv[c + 64], a2));
+            const double b3 = fma(-vrow, sw[c + 96], fma(-wrow, sv[c + 96], a3));
+            Arow[c] = b0; Arow[c + 32] = b1; Arow[c + 64] = b2; Arow[c + 96] = b3;
+            dot = fma(b0, sn[c], dot);
+            dot = fma(b1, sn[c + 32], dot);
+            dot = fma(b2, sn[c + 64], dot);
+            dot = fma(b3, sn[c + 96], dot);
+        }
+        for (; c < d; c += 32) {
             const double a = fma(-vrow, sw[c], fma(-wrow, sv[c], Arow[c]));
             Arow[c] = a;
             dot = fma(a, sn[c], dot);

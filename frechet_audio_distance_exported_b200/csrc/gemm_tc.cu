@@ -23,6 +23,7 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -35,6 +36,7 @@ namespace fadb {
 struct GemmParams {
     CUtensorMap tmA[2];   // activations hi, lo : dims (C, W, H, B)
     CUtensorMap tmB[2];   // weights hi, lo     : dims (Ktot, N)
+    CUtensorMap tmH;      // halo mode: activations hi with box (64 ch, 16 px, 18 rows, 1 image)
     int W, H, B;
     int BW, BH, BB;       // box; BW*BH*BB == 128
     int tiles_w, tiles_h, tiles_b, tiles_n;
@@ -46,6 +48,9 @@ struct GemmParams {
     int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
     int kb_begin, kb_end; // K-block range of this launch (whole K unless the exact-accumulation path splits it)
     int raw;              // 0 = fused epilogue; 1 = write raw fp32 partial sums; 2 = add them to out_f32
+    int dbg_skip_a;       // PROFILING ONLY (FADB_DEBUG_SKIP_A): load the A tile for tap 0 only -> wrong results, shows A-traffic cost
+    int halo;             // 1 = halo mode: one activation tile per channel block feeds all 9 taps
+    int b_stages;         // halo mode: depth of the separate B ring
     int resb;             // 1 = the whole B operand (all K blocks of the single N tile) stays resident in smem
     int relu;
     int pool;             // 0 none, 1 max, 2 avg
@@ -61,6 +66,7 @@ constexpr int kThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // one 128-byte swizzle atom of bf16
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16384
+constexpr int kHaloBytes = 18 * 16 * 128;         // halo tile: 18 rows x 16 pixels x 64 channels bf16 = 36864
 
 template <int BN>
 struct GemmCfg {
@@ -68,7 +74,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kMaxStages = 8;
     static constexpr int kTmemCols = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
-    static constexpr int kExtraBytes = 256 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr int kExtraBytes = 512 /*barriers*/ + 1024 /*alignment slack*/;
     static constexpr int kMaxSmemBytes = 232448;                      // 227 KB: the per-CTA opt-in maximum
     static int stages_for(int budget_bytes) {
         int s = budget_bytes / kStageBytes;
@@ -206,6 +212,22 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// Halo mode: the A operand of tap (dy, dx) is a VIEW into one shared-memory halo tile of 18 rows x 16 pixels
+// x 128 B.  An accumulator row group (8 pixels of one image row) is 8 consecutive 128-B rows of the halo tile;
+// consecutive groups are one halo row (2048 B) apart -> SBO = 2048.  The view starts dx rows into a 1024-B
+// swizzle atom; measured on B200: the 128-B swizzle is applied to ABSOLUTE shared-memory address bits (the same
+// bits TMA used when it wrote the tile), so the descriptor's base-offset field must stay 0 — setting it to the
+// row phase gives wrong results.
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(2048 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -224,17 +246,21 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     const uint32_t base = (raw_addr + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-B alignment
     uint8_t* smem = smem_raw + (base - raw_addr);
 
-    // layout: [resident B: nkb x kBBytes (resb only)] [stages] [barriers]
+    // layout: [resident B: nkb x kBBytes (resb only)] [stages] ([halo mode: B ring]) [barriers]
     const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * Cfg::kBBytes : 0;
-    const int stage_pitch = p.resb ? kABytes : Cfg::kStageBytes;
+    const int stage_pitch = p.halo ? kHaloBytes : (p.resb ? kABytes : Cfg::kStageBytes);
     const uint32_t stage_base = base + res_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + res_bytes + kStages * stage_pitch);
+    const uint32_t bring_base = stage_base + kStages * stage_pitch;           // halo mode only
+    const int bring_bytes = (p.halo && !p.resb) ? p.b_stages * Cfg::kBBytes : 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + res_bytes + kStages * stage_pitch + bring_bytes);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages]
     const uint32_t bar_tfull = bar_empty + 8 * kStages;              // [2]
     const uint32_t bar_tempty = bar_tfull + 16;                      // [2]
     const uint32_t bar_bres = bar_tempty + 16;                       // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+    const uint32_t bar_bfull = bar_bres + 8;                         // [8]  halo mode B ring
+    const uint32_t bar_bempty = bar_bfull + 64;                      // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5 + 16);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -257,6 +283,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             mbar_init(bar_tempty + 8 * s, 4);                        // one arrive per epilogue warp
         }
         mbar_init(bar_bres, 1);
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
@@ -269,7 +299,35 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     if (warp == 0) {
         // ======================= TMA producer (whole warp runs the loop; one elected lane issues) =====
-        {
+        if (p.halo) {
+            // halo mode: ONE activation load per (tile, channel block) serves all 9 taps
+            int stage = 0;
+            uint32_t phase = 0;
+            if (p.resb && blockIdx.x < p.num_tiles) {
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_bres, (uint32_t)res_bytes);
+                    for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
+                        tma_load_2d(&p.tmB[0], bar_bres, base + (kbg - p.kb_begin) * Cfg::kBBytes, kbg * kBlockK, 0);
+                }
+                __syncwarp();
+            }
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int m = tile / p.tiles_n;
+                const int wt = m % p.tiles_w; m /= p.tiles_w;
+                const int ht = m % p.tiles_h;
+                const int bt = m / p.tiles_h;
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)kHaloBytes);
+                        tma_load_4d(&p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes, cb * kBlockK,
+                                    wt * p.BW - 1, ht * p.BH - 1, bt);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else {
             int stage = 0;
             uint32_t phase = 0;
             if (p.resb && blockIdx.x < p.num_tiles) {
@@ -300,14 +358,87 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
-                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                        const bool skip_a = p.dbg_skip_a && tap > 0;
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(stage_pitch - (skip_a ? kABytes : 0)));
+                        if (!skip_a) tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
                         if (!p.resb) tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
+        }
+    } else if (warp == 3) {
+        // ======================= halo mode: weight (B) producer on its own warp =======================
+        if (p.halo && !p.resb) {
+            int bs = 0;
+            uint32_t bphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.tiles_n) * BN;
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(bar_bfull + 8 * bs, (uint32_t)Cfg::kBBytes);
+                            tma_load_2d(&p.tmB[0], bar_bfull + 8 * bs, bring_base + bs * Cfg::kBBytes,
+                                        (tap * p.cin_blocks + cb) * kBlockK, n0);
+                        }
+                        __syncwarp();
+                        if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && p.halo) {
+        // ======================= MMA issuer, halo mode =======================
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                                   (uint32_t(kTileM >> 4) << 24);
+        int stage = 0, bs = 0, it = 0;
+        uint32_t phase = 0, bphase = 0;
+        if (p.resb && blockIdx.x < p.num_tiles) {
+            mbar_wait(bar_bres, 0, p.err_flag);
+            tc_fence_after();
+        }
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            uint32_t first = 1;
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                mbar_wait(bar_full + 8 * stage, phase, p.err_flag);         // halo tile landed
+                tc_fence_after();
+                const uint32_t ha = stage_base + stage * kHaloBytes;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3, dx = tap - dy * 3;              // 0..2 = offset + 1
+                    uint32_t sb;
+                    if (p.resb) {
+                        sb = base + (tap * p.cin_blocks + cb) * Cfg::kBBytes;
+                    } else {
+                        mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
+                        tc_fence_after();
+                        sb = bring_base + bs * Cfg::kBBytes;
+                    }
+                    const uint64_t da = make_halo_desc(ha + (dy * 16 + dx) * 128);
+                    const uint64_t db = make_sw128_desc(sb);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                        if (!p.resb) umma_commit(bar_bempty + 8 * bs);
+                    }
+                    __syncwarp();
+                    first = 0;
+                    if (!p.resb) { if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; } }
+                }
+                if (elect_one()) umma_commit(bar_empty + 8 * stage);        // halo tile free again
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            if (elect_one()) umma_commit(bar_tfull + 8 * as);
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) =======
@@ -626,11 +757,19 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     FADB_REQUIRE(L.N % BN == 0 && L.N >= 64, "Cout=%d must be a multiple of 64", L.N);
     FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
 
-    // pick the 128-pixel box: full rows first, then rows, then images
+    // halo mode (single-pass 3x3 layers on maps at least 8 wide / 16 high): 8 x 16 pixel tiles whose input is ONE
+    // 18 x 16-pixel halo box per channel block instead of nine shifted boxes -> 4x less L2 -> SM traffic for
+    // the A operand.  Only used when H is large against the 16-row tile (few wasted rows).
+    int halo = 0;
     int BW = 1, BH = 1, BB = 1;
-    if (io.W >= kTileM || (io.taps == 1 && io.H == 1 && io.B == 1)) {
+    if (h->halo && io.taps == 9 && npass == 1 && io.W % 8 == 0 && io.H >= 16 &&
+        double((io.H + 15) / 16 * 16) / io.H <= 1.13) {
+        halo = 1;
+        BW = 8; BH = 16; BB = 1;
+    } else if (io.W >= kTileM || (io.taps == 1 && io.H == 1 && io.B == 1)) {
         BW = kTileM;      // rows of a linear layer: the box may overhang the tensor, TMA zero-fills
     } else {
+        // pick the 128-pixel box: full rows first, then rows, then images
         BW = 1;
         while (BW * 2 <= io.W && BW * 2 <= kTileM) BW *= 2;        // largest power of two <= W
         FADB_REQUIRE(BW == io.W, "W=%d must be a power of two below 128 or >= 128", io.W);
@@ -661,6 +800,9 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     GemmParams p;
     memset(&p, 0, sizeof(p));
     FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB));
+    if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, 16, 18, 1));
+    else p.tmH = p.tmA[0];
+    p.halo = halo;
     FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN));
     if (npass == 3) {
         FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB));
@@ -691,6 +833,11 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.out_lo = (h->precision == FADB_PREC_BF16X3) ? io.out_lo : nullptr;
     p.out_f32 = io.out_f32;
     p.err_flag = h->err_flag;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("FADB_DEBUG_SKIP_A"); dbg = e ? atoi(e) : 0; }
+        p.dbg_skip_a = dbg;
+    }
     FADB_REQUIRE(p.out_f32 || p.out_hi, "layer has no output buffer");
 
     const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
@@ -704,20 +851,35 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     auto launch = [&](const GemmParams& q) {
         GemmParams pp = q;
         const int b_bytes = BN * kBlockK * 2;
-        // resident-B: short-K layers whose whole weight slab fits next to >= 4 A stages (VGGish conv2, CNN14
-        // block1.conv2): halves the L2 -> SM traffic of a layer that is L2-bandwidth bound, not MMA bound
         const int res = (pp.kb_end - pp.kb_begin) * b_bytes;
-        pp.resb = (h->resident_b && npass == 1 && pp.tiles_n == 1 && res + 4 * kABytes <= budget) ? 1 : 0;
         int smem;
-        if (pp.resb) {
-            pp.stages = (budget - res) / kABytes;
-            if (pp.stages > 8) pp.stages = 8;
-            smem = res + pp.stages * kABytes + GemmCfg<64>::kExtraBytes;
+        if (pp.halo && pp.raw == 0) {
+            pp.resb = (h->resident_b && pp.tiles_n == 1 && res + 2 * kHaloBytes <= budget) ? 1 : 0;
+            if (pp.resb) {
+                pp.b_stages = 0;
+                pp.stages = (budget - res) / kHaloBytes;
+                if (pp.stages > 4) pp.stages = 4;
+                smem = res + pp.stages * kHaloBytes + GemmCfg<64>::kExtraBytes;
+            } else {
+                pp.b_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+                pp.stages = (budget - pp.b_stages * b_bytes) / kHaloBytes;
+                if (pp.stages > 4) pp.stages = 4;
+                smem = pp.stages * kHaloBytes + pp.b_stages * b_bytes + GemmCfg<64>::kExtraBytes;
+            }
         } else {
-            pp.stages = budget / (kABytes + b_bytes);
-            if (pp.stages > 8) pp.stages = 8;
-            if (pp.stages < 2) pp.stages = 2;
-            smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes;
+            pp.halo = 0;
+            // resident-B: short-K layers whose whole weight slab fits next to >= 4 A stages
+            pp.resb = (h->resident_b > 1 && npass == 1 && pp.tiles_n == 1 && res + 4 * kABytes <= budget) ? 1 : 0;
+            if (pp.resb) {
+                pp.stages = (budget - res) / kABytes;
+                if (pp.stages > 8) pp.stages = 8;
+                smem = res + pp.stages * kABytes + GemmCfg<64>::kExtraBytes;
+            } else {
+                pp.stages = budget / (kABytes + b_bytes);
+                if (pp.stages > 8) pp.stages = 8;
+                if (pp.stages < 2) pp.stages = 2;
+                smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes;
+            }
         }
         if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, smem, st>>>(pp);
         else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, smem, st>>>(pp);

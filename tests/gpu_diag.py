@@ -44,6 +44,9 @@ def sec_conv():
         ("conv 1x129x8 64->128 avg", 1, 129, 8, 64, 128, 3, 1, 2),
         ("conv 2x32x2 128->256", 2, 32, 2, 128, 256, 3, 1, 0),
         ("conv 1x40x64 64->64 avg", 1, 40, 64, 64, 64, 3, 1, 2),
+        ("halo 2x32x16 128->256", 2, 32, 16, 128, 256, 3, 1, 0),
+        ("halo 1x64x8 192->64 max", 1, 64, 8, 192, 64, 3, 1, 1),
+        ("halo 3x60x16 64->128 avg", 3, 60, 16, 64, 128, 3, 1, 2),
     ]
     g = torch.Generator().manual_seed(1)
     for prec in ("bf16", "bf16x3"):

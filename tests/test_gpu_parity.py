@@ -58,6 +58,9 @@ CONV_CASES = [
     (1, 129, 8, 64, 128, 3, 1, 2),       # CNN14 block4 geometry: odd H, floor pooling
     (3, 32, 2, 128, 256, 3, 1, 0),       # CNN14 block6 geometry
     (1, 40, 64, 64, 64, 3, 1, 2),        # CNN14 block1 geometry, Cout = 64 tile
+    (2, 32, 16, 128, 256, 3, 1, 0),      # halo mode, weights streamed through the B ring (2 channel blocks)
+    (1, 64, 8, 192, 64, 3, 1, 1),        # halo mode, W = 8 (right halo column is out of bounds), 3 channel blocks
+    (3, 60, 16, 64, 128, 3, 1, 2),       # halo mode + resident weights, ragged H (60 = 3 tiles of 16 + 12)
 ]
 
 
