@@ -91,8 +91,8 @@ struct fadb_handle {
     int device = 0;
     int sm_count = 148;
     int precision = FADB_PREC_BF16;
-    int max_batch = 4096;           // VGGish patches per internal batch
-    int max_batch_cnn14 = 32;       // CNN14 clips per internal batch
+    int max_batch = 16384;          // VGGish patches per internal batch (fewer, larger launches: ~5 us gap each)
+    int max_batch_cnn14 = 128;      // CNN14 clips per internal batch
     int gemm_smem_budget = 231168;  // bytes of smem for resident weights + pipeline stages per GEMM CTA
                                     // (227 KB opt-in maximum minus barriers/alignment slack)
     int fused_front = 1;            // VGGish: PCM -> conv1 output in one kernel (features stay in shared memory)
