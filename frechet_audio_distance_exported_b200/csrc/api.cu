@@ -324,8 +324,8 @@ static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* 
     return vggish_tc_layers(h, a1, a1_lo_plane(h, 0), P, emb, st);
 }
 
-// PCM -> embeddings for VGGish, chunked.  In overlap mode the front end + conv1 (fp64 / fp32 CUDA-core work)
-// of chunk i+1 run on a side stream while the tcgen05 layers of chunk i own the tensor pipes.
+// PCM -> embeddings for VGGish, chunked.  (A side stream running front end + conv1 of chunk i+1 under the tcgen05
+// layers of chunk i was measured and gave no gain at any smem budget / stream priority; removed.)
 static int vggish_embed_pcm(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                             int64_t rows, float* emb, cudaStream_t st) {
     const int d = 128;
@@ -333,46 +333,21 @@ static int vggish_embed_pcm(fadb_handle* h, const float* pcm, int64_t n_clips, i
     const int64_t batch = (h->precision == FADB_PREC_BF16X3 && h->max_batch > 4096) ? 4096 : h->max_batch;
     int64_t cpc = batch / rows;                         // clips per chunk
     FADB_REQUIRE(cpc >= 1, "max_batch %d smaller than patches per clip %lld", h->max_batch, (long long)rows);
-    const size_t feat_bytes = (size_t)cpc * rows * 96 * 64 * sizeof(float);
-    FADB_CHECK(h->ws_feats.reserve(feat_bytes));
-    const int64_t nchunks = (n_clips + cpc - 1) / cpc;
-    const bool overlap = h->overlap && nchunks > 1;
-    if (!overlap) {
-        for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
-            const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
-            if (h->fused_front) {
-                FADB_CHECK(reserve_a1(h, 0));
-                __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
-                FADB_CHECK(launch_vggish_front_conv1(h, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride, a1,
-                                                     a1_lo_plane(h, 0), st));
-                FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0), nc * rows, emb + c0 * rows * d, st));
-            } else {
-                FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride,
-                                           h->ws_feats.as<float>(), st));
-                FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
-            }
-        }
-        return FADB_OK;
-    }
-    FADB_CHECK(h->ws_feats2.reserve(feat_bytes));
-    FADB_CHECK(reserve_a1(h, 0));
-    FADB_CHECK(reserve_a1(h, 1));
-    float* feats[2] = {h->ws_feats.as<float>(), h->ws_feats2.as<float>()};
-    cudaStream_t aux = h->aux_stream;
-    FADB_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));                 // inputs (and prior use of the workspaces) ordered
-    FADB_CUDA_CHECK(cudaStreamWaitEvent(aux, h->ev_fork, 0));
-    int64_t i = 0;
-    for (int64_t c0 = 0; c0 < n_clips; c0 += cpc, ++i) {
-        const int b = (int)(i & 1);
+    for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
         const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
-        __nv_bfloat16* a1 = h->ws_a1[b].as<__nv_bfloat16>();
-        if (i >= 2) FADB_CUDA_CHECK(cudaStreamWaitEvent(aux, h->ev_done[b], 0));      // a1[b] / feats[b] free again
-        FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride, feats[b], aux));
-        FADB_CHECK(launch_conv1_vggish(h, feats[b], nc * rows, a1, a1_lo_plane(h, b), aux));
-        FADB_CUDA_CHECK(cudaEventRecord(h->ev_pre[b], aux));
-        FADB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_pre[b], 0));
-        FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, b), nc * rows, emb + c0 * rows * d, st));
-        FADB_CUDA_CHECK(cudaEventRecord(h->ev_done[b], st));
+        if (h->fused_front) {
+            // front end + conv1 in one kernel: the fp32 features never touch HBM
+            FADB_CHECK(reserve_a1(h, 0));
+            __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
+            FADB_CHECK(launch_vggish_front_conv1(h, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride, a1,
+                                                 a1_lo_plane(h, 0), st));
+            FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0), nc * rows, emb + c0 * rows * d, st));
+        } else {
+            FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 96 * 64 * sizeof(float)));
+            FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride,
+                                       h->ws_feats.as<float>(), st));
+            FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
+        }
     }
     return FADB_OK;
 }
@@ -481,21 +456,6 @@ int fadb_create(fadb_handle** out, int device) {
         FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
         FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_compute[i], cudaEventDisableTiming));
     }
-    {
-        // side stream at the LOWEST priority: the tcgen05 layers on the caller's stream get CTAs first,
-        // front-end / conv1 CTAs of the next chunk fill whatever an SM has left
-        int lo = 0, hi = 0;
-        FADB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        int prio = lo;
-        if (const char* e = getenv("FADB_AUX_PRIO")) prio = atoi(e) ? lo : 0;
-        FADB_CUDA_CHECK(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio));
-    }
-    FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-        FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
-        FADB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
-    if (const char* e = getenv("FADB_OVERLAP")) h->overlap = atoi(e);
     if (const char* e = getenv("FADB_GEMM_SMEM")) h->gemm_smem_budget = atoi(e);
     if (const char* e = getenv("FADB_RESIDENT_B")) h->resident_b = atoi(e);
     if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
@@ -516,13 +476,7 @@ void fadb_destroy(fadb_handle* h) {
     h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    for (int i = 0; i < 2; ++i) {
-        if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
-        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
-    }
-    h->ws_feats2.release(); h->ws_a1[0].release(); h->ws_a1[1].release();
+    h->ws_a1[0].release();
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);

@@ -98,7 +98,6 @@ struct fadb_handle {
     int fused_front = 1;            // VGGish: PCM -> conv1 output in one kernel (features stay in shared memory)
     int halo = 1;                   // 3x3 layers on large maps: one halo tile per channel block feeds all 9 taps
     int resident_b = 1;             // keep short-K weight slabs resident in smem (see gemm_tc.cu)
-    int overlap = 0;                // (experiment, default off: measured no gain) run front end + conv1 of chunk i+1 on a side stream under the GEMMs of chunk i
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;
     int64_t launches = 0;
@@ -117,12 +116,7 @@ struct fadb_handle {
     fadb::DevBuf weight_pool;                          // backing store of all packed weights
 
     // activation workspace
-    fadb::DevBuf ws_feats2;     // second feature buffer (overlap mode)
-    fadb::DevBuf ws_a1[2];      // conv1 outputs, double-buffered (overlap mode)
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_pre[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr;
+    fadb::DevBuf ws_a1[1];      // conv1 output (input of the first tensor-core layer)
     fadb::DevBuf ws_feats;      // fp32 features of one batch
     fadb::DevBuf ws_act[2];     // ping-pong bf16 activations (hi plane followed by lo plane)
     fadb::DevBuf ws_misc;       // pooled vectors etc.

@@ -48,10 +48,9 @@ struct GemmParams {
     int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
     int kb_begin, kb_end; // K-block range of this launch (whole K unless the exact-accumulation path splits it)
     int raw;              // 0 = fused epilogue; 1 = write raw fp32 partial sums; 2 = add them to out_f32
-    int dbg_skip_a;       // PROFILING ONLY (FADB_DEBUG_SKIP_A): load the A tile for tap 0 only -> wrong results, shows A-traffic cost
     int halo;             // 1 = halo mode: one activation tile per channel block feeds all 9 taps
     int b_stages;         // halo mode: depth of the separate B ring
-    int resb;             // 1 = the whole B operand (all K blocks of the single N tile) stays resident in smem
+    int resb;             // halo mode: 1 = all weights of the (single) N tile stay resident in smem
     int relu;
     int pool;             // 0 none, 1 max, 2 avg
     int Ho, Wo;           // output spatial dims (after pooling)
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     // layout: [resident B: nkb x kBBytes (resb only)] [stages] ([halo mode: B ring]) [barriers]
     const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * Cfg::kBBytes : 0;
-    const int stage_pitch = p.halo ? kHaloBytes : (p.resb ? kABytes : Cfg::kStageBytes);
+    const int stage_pitch = p.halo ? kHaloBytes : Cfg::kStageBytes;
     const uint32_t stage_base = base + res_bytes;
     const uint32_t bring_base = stage_base + kStages * stage_pitch;           // halo mode only
     const int bring_bytes = (p.halo && !p.resb) ? p.b_stages * Cfg::kBBytes : 0;
@@ -330,15 +329,6 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         } else {
             int stage = 0;
             uint32_t phase = 0;
-            if (p.resb && blockIdx.x < p.num_tiles) {
-                // weights of the (single) N tile: loaded once per CTA, reused by every tile
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(bar_bres, (uint32_t)res_bytes);
-                    for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
-                        tma_load_2d(&p.tmB[0], bar_bres, base + (kbg - p.kb_begin) * Cfg::kBBytes, kbg * kBlockK, 0);
-                }
-                __syncwarp();
-            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int m = tile / p.tiles_n;
                 const int n0 = (tile - m * p.tiles_n) * BN;
@@ -358,10 +348,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     if (elect_one()) {
-                        const bool skip_a = p.dbg_skip_a && tap > 0;
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(stage_pitch - (skip_a ? kABytes : 0)));
-                        if (!skip_a) tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                        if (!p.resb) tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
+                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                        tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -449,10 +438,6 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            if (p.resb && blockIdx.x < p.num_tiles) {
-                mbar_wait(bar_bres, 0, p.err_flag);
-                tc_fence_after();
-            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -464,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     tc_fence_after();
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     const uint64_t da = make_sw128_desc(sa);
-                    const uint64_t db = make_sw128_desc(p.resb ? base + (kb - p.kb_begin) * Cfg::kBBytes : sa + kABytes);
+                    const uint64_t db = make_sw128_desc(sa + kABytes);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
@@ -833,11 +818,6 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.out_lo = (h->precision == FADB_PREC_BF16X3) ? io.out_lo : nullptr;
     p.out_f32 = io.out_f32;
     p.err_flag = h->err_flag;
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("FADB_DEBUG_SKIP_A"); dbg = e ? atoi(e) : 0; }
-        p.dbg_skip_a = dbg;
-    }
     FADB_REQUIRE(p.out_f32 || p.out_hi, "layer has no output buffer");
 
     const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
@@ -868,18 +848,11 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             }
         } else {
             pp.halo = 0;
-            // resident-B: short-K layers whose whole weight slab fits next to >= 4 A stages
-            pp.resb = (h->resident_b > 1 && npass == 1 && pp.tiles_n == 1 && res + 4 * kABytes <= budget) ? 1 : 0;
-            if (pp.resb) {
-                pp.stages = (budget - res) / kABytes;
-                if (pp.stages > 8) pp.stages = 8;
-                smem = res + pp.stages * kABytes + GemmCfg<64>::kExtraBytes;
-            } else {
-                pp.stages = budget / (kABytes + b_bytes);
-                if (pp.stages > 8) pp.stages = 8;
-                if (pp.stages < 2) pp.stages = 2;
-                smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes;
-            }
+            pp.resb = 0;
+            pp.stages = budget / (kABytes + b_bytes);
+            if (pp.stages > 8) pp.stages = 8;
+            if (pp.stages < 2) pp.stages = 2;
+            smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes;
         }
         if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, smem, st>>>(pp);
         else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, smem, st>>>(pp);
