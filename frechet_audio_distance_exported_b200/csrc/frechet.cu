@@ -19,6 +19,8 @@
 //     the symmetric matrix-vector product of step k+1, so the trailing matrix is read+written once
 //     per step; the O(d) vector algebra is recomputed by every CTA instead of synchronising the grid
 //   * bisection: one thread per eigenvalue.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace fadb {
@@ -260,30 +262,28 @@ __global__ void symmetrize_kernel(double* __restrict__ A, int d) {
 //   out: A updated for rows/cols >= k+2, v_{k+1}, beta_{k+1}, p_{k+1}, diag[k+1], off[k+1]
 // vec layout: [v (d) | p (d) | beta (1)] , ping-pong by step parity.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) tridiag_step_kernel(double* __restrict__ A, int d, int k,
-                                                           const double* __restrict__ vec_in,
-                                                           double* __restrict__ vec_out, double* __restrict__ diag,
-                                                           double* __restrict__ off) {
-    extern __shared__ __align__(16) double tsm[];
+// NOTE: no __restrict__ / read-only-cache loads on A and the vectors here — inside the persistent kernel they are
+// written by other CTAs one grid barrier earlier, so they must be read through the coherent L2 path (__ldcg).
+__device__ __forceinline__ void tridiag_step(double* A, int d, int k, const double* vec_in, double* vec_out,
+                                             double* diag, double* off, double* tsm, double* red) {
     double* sv = tsm;            // v_k          [d]
     double* sw = tsm + d;        // w_k          [d]
     double* sn = tsm + 2 * d;    // v_{k+1}      [d]
-    __shared__ double red[33];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int r = k + 1;                         // row that becomes final in this step
     const double* vin = vec_in;
     const double* pin = vec_in + d;
-    const double beta = vec_in[2 * d];
+    const double beta = __ldcg(vec_in + 2 * d);
 
     // (a) K = beta (v.p)/2 ; w = p - K v
     double part = 0.0;
     for (int i = r + tid; i < d; i += nt) {
-        const double v = (i >= r) ? vin[i] : 0.0;
+        const double v = (i >= r) ? __ldcg(vin + i) : 0.0;
         sv[i] = v;
-        part += v * pin[i];
+        part += v * __ldcg(pin + i);
     }
     const double K = 0.5 * beta * block_sum(part, red);
-    for (int i = r + tid; i < d; i += nt) sw[i] = pin[i] - K * sv[i];
+    for (int i = r + tid; i < d; i += nt) sw[i] = __ldcg(pin + i) - K * sv[i];
     __syncthreads();
 
     // (b) updated row r -> diag[r], x = row[r+1:], next reflector
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(512) tridiag_step_kernel(double* __restrict__ 
     const double* Ar = A + (size_t)r * d;
     part = 0.0;
     for (int c = r + 1 + tid; c < d; c += nt) {
-        const double x = fma(-vr, sw[c], fma(-wr, sv[c], Ar[c]));
+        const double x = fma(-vr, sw[c], fma(-wr, sv[c], __ldcg(Ar + c)));
         sn[c] = x;
         part += x * x;
     }
@@ -310,12 +310,13 @@ __global__ void __launch_bounds__(512) tridiag_step_kernel(double* __restrict__ 
     }
     __syncthreads();
     if (tid == 0 && m >= 1) sn[r + 1] = reflect ? (x0 - alpha) : 0.0;
+    if (tid == 1) sn[r] = 0.0;                   // the vector path of phase (c) may touch column r
     if (!reflect)
         for (int c = r + 2 + tid; c < d; c += nt) sn[c] = 0.0;
     __syncthreads();
     if (blockIdx.x == 0) {
         if (tid == 0) {
-            diag[r] = fma(-2.0 * vr, wr, Ar[r]);
+            diag[r] = fma(-2.0 * vr, wr, __ldcg(Ar + r));
             if (m >= 1) off[r] = alpha;
             vec_out[2 * d] = bnext;
         }
@@ -326,29 +327,61 @@ __global__ void __launch_bounds__(512) tridiag_step_kernel(double* __restrict__ 
     const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
     const int first = r + 1;
     double* pout = vec_out + d;
-    for (int row = first + blockIdx.x * nwarp + warp; row < d; row += gridDim.x * nwarp) {
+    // fixed row ownership (row -> global warp row % W) so a row is always touched by the same SM; loads bypass
+    // L1 anyway (__ldcg): L1 is not coherent across SMs and this runs inside a persistent kernel
+    for (int row = blockIdx.x * nwarp + warp; row < d; row += gridDim.x * nwarp) {
+        if (row < first) continue;
         double* Arow = A + (size_t)row * d;
         const double vrow = sv[row], wrow = sw[row];
         double dot = 0.0;
-        // 4 independent 256-byte row segments in flight per warp: all loads are issued before the first
-        // store (the one-element-per-iteration form serialised on the L2 round trip of every segment)
-        int c = first + lane;
-        for (; c + 96 < d; c += 128) {
-            const double a0 = Arow[c], a1 = Arow[c + 32], a2 = Arow[c + 64], a3 = Arow[c + 96];
-            const double b0 = fma(-vrow, sw[c], fma(-wrow, sv[c], a0));
-            const double b1 = fma(-vrow, sw[c + 32], fma(-wrow, sv[c + 32], a1));
-            const double b2 = fma(-vrow, sw[c + 64], fma(-wrow, sv[c + 64], a2));
-            const double b3 = fma(-vrow, sw[c + 96], fma(-wrow, sv[c + 96], a3));
-            Arow[c] = b0; Arow[c + 32] = b1; Arow[c + 64] = b2; Arow[c + 96] = b3;
-            dot = fma(b0, sn[c], dot);
-            dot = fma(b1, sn[c + 32], dot);
-            dot = fma(b2, sn[c + 64], dot);
-            dot = fma(b3, sn[c + 96], dot);
-        }
-        for (; c < d; c += 32) {
-            const double a = fma(-vrow, sw[c], fma(-wrow, sv[c], Arow[c]));
-            Arow[c] = a;
-            dot = fma(a, sn[c], dot);
+        if ((d & 1) == 0) {
+            // even d: rows are 16-byte aligned -> 128-bit loads, 8 x 512 B in flight per warp (the streaming part is
+            // bound by bytes in flight per SM against the L2 round trip, not by L2 bandwidth).  Starts at the even
+            // column <= first; the extra column (the finished column r) is updated harmlessly, sn[r] = 0.
+            const int c0 = first & ~1;
+            int c = c0 + 2 * lane;
+            for (; c + 448 < d; c += 512) {
+                double2 a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = __ldcg(reinterpret_cast<const double2*>(Arow + c + 64 * u));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int cc = c + 64 * u;
+                    a[u].x = fma(-vrow, sw[cc], fma(-wrow, sv[cc], a[u].x));
+                    a[u].y = fma(-vrow, sw[cc + 1], fma(-wrow, sv[cc + 1], a[u].y));
+                    *reinterpret_cast<double2*>(Arow + cc) = a[u];
+                    dot = fma(a[u].x, sn[cc], dot);
+                    dot = fma(a[u].y, sn[cc + 1], dot);
+                }
+            }
+            for (; c < d; c += 64) {
+                double2 a = __ldcg(reinterpret_cast<const double2*>(Arow + c));
+                a.x = fma(-vrow, sw[c], fma(-wrow, sv[c], a.x));
+                a.y = fma(-vrow, sw[c + 1], fma(-wrow, sv[c + 1], a.y));
+                *reinterpret_cast<double2*>(Arow + c) = a;
+                dot = fma(a.x, sn[c], dot);
+                dot = fma(a.y, sn[c + 1], dot);
+            }
+        } else {
+            int c = first + lane;
+            for (; c + 96 < d; c += 128) {
+                const double a0 = __ldcg(Arow + c), a1 = __ldcg(Arow + c + 32), a2 = __ldcg(Arow + c + 64),
+                             a3 = __ldcg(Arow + c + 96);
+                const double b0 = fma(-vrow, sw[c], fma(-wrow, sv[c], a0));
+                const double b1 = fma(-vrow, sw[c + 32], fma(-wrow, sv[c + 32], a1));
+                const double b2 = fma(-vrow, sw[c + 64], fma(-wrow, sv[c + 64], a2));
+                const double b3 = fma(-vrow, sw[c + 96], fma(-wrow, sv[c + 96], a3));
+                Arow[c] = b0; Arow[c + 32] = b1; Arow[c + 64] = b2; Arow[c + 96] = b3;
+                dot = fma(b0, sn[c], dot);
+                dot = fma(b1, sn[c + 32], dot);
+                dot = fma(b2, sn[c + 64], dot);
+                dot = fma(b3, sn[c + 96], dot);
+            }
+            for (; c < d; c += 32) {
+                const double a = fma(-vrow, sw[c], fma(-wrow, sv[c], __ldcg(Arow + c)));
+                Arow[c] = a;
+                dot = fma(a, sn[c], dot);
+            }
         }
         dot = warp_sum(dot);
         if (lane == 0) pout[row] = bnext * dot;
@@ -357,8 +390,23 @@ __global__ void __launch_bounds__(512) tridiag_step_kernel(double* __restrict__ 
         for (int c = tid; c <= r && c < d; c += nt) pout[c] = 0.0;
 }
 
-__global__ void tridiag_last_kernel(const double* __restrict__ A, int d, double* __restrict__ diag) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) diag[d - 1] = A[(size_t)(d - 1) * d + (d - 1)];
+// All Householder steps in ONE cooperative launch: a grid-wide barrier separates step k (which leaves p_{k+1}
+// complete in global memory) from step k+1.  One launch per step cost ~6 us of launch + ramp per step
+// (2047 steps at d = 2048); the grid barrier costs ~2 us.
+__global__ void __launch_bounds__(512) tridiag_persistent_kernel(double* __restrict__ A, int d, double* __restrict__ vec0,
+                                                                 double* __restrict__ vec1, double* __restrict__ diag,
+                                                                 double* __restrict__ off) {
+    extern __shared__ __align__(16) double tsm[];
+    __shared__ double red[33];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    int step = 0;
+    for (int k = -1; k <= d - 3; ++k, ++step) {
+        const double* vin = (step & 1) ? vec1 : vec0;
+        double* vout = (step & 1) ? vec0 : vec1;
+        tridiag_step(A, d, k, vin, vout, diag, off, tsm, red);
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) diag[d - 1] = A[(size_t)(d - 1) * d + (d - 1)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,24 +560,20 @@ int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const do
         const size_t smem = 3 * (size_t)d * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
-            FADB_CUDA_CHECK(cudaFuncSetAttribute(tridiag_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            FADB_CUDA_CHECK(cudaFuncSetAttribute(tridiag_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  3 * 8192 * (int)sizeof(double)));
             FADB_CUDA_CHECK(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  2 * 8192 * (int)sizeof(double)));
             attr_set = true;
         }
-        int step = 0;
-        for (int k = -1; k <= d - 3; ++k, ++step) {
-            const double* vin = (step & 1) ? vec1 : vec0;
-            double* vout = (step & 1) ? vec0 : vec1;
-            const int rows = d - (k + 2);
-            int grid = (rows + 15) / 16;                 // 16 warps per CTA, one row per warp per sweep
-            if (grid > h->sm_count) grid = h->sm_count;
-            if (grid < 1) grid = 1;
-            tridiag_step_kernel<<<grid, 512, smem, st>>>(B, d, k, vin, vout, diag, off);
-            h->launches++;
-        }
-        tridiag_last_kernel<<<1, 32, 0, st>>>(B, d, diag);
+        int grid = (d + 15) / 16;                        // 16 warps per CTA, one row per warp per sweep
+        if (grid > h->sm_count) grid = h->sm_count;
+        if (grid < 1) grid = 1;
+        double* Bm = B;
+        int dd_ = d;
+        void* args[] = {(void*)&Bm, (void*)&dd_, (void*)&vec0, (void*)&vec1, (void*)&diag, (void*)&off};
+        FADB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tridiag_persistent_kernel, dim3(grid), dim3(512), args,
+                                                    smem, st));
         h->launches++;
     }
     // ---- eigenvalues + trace of the square root
