@@ -297,3 +297,24 @@ def test_vggish_fad_config0_scale_properties(vgg_sd):
     mu3, s3 = eng.stats_finalize(acc3, 128)
     assert float((s1 - s3).abs().max() / s1.abs().max()) < 1e-10
     assert abs(float(eng.frechet(mu1, s1, mu3, s3)[0])) < 1e-6 * float(s1.diagonal().sum())
+
+
+def test_host_streaming_multi_chunk_matches_single_call(vgg_sd):
+    """accumulate_clips from HOST memory in several double-buffered chunks (copy stream + events) gives exactly
+    the statistics of one device-resident call; ragged last chunk; pinned and pageable sources."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd)
+    eng = fad.engine
+    n = 2 * 16000 + 400
+    clips = torch.from_numpy(np.stack([synth.eval_clip(i, n, 16000) for i in range(11)]))
+    ref = eng.new_acc()
+    eng.stats_accumulate(eng.embed_pcm(clips.cuda()), ref)
+    for src in (clips, clips.pin_memory()):
+        acc = eng.new_acc()
+        fad.accumulate_clips(src, acc, chunk_clips=4)          # 4 + 4 + 3 clips
+        torch.cuda.synchronize()
+        assert float(acc[0]) == 22.0
+        assert float((acc - ref).abs().max() / ref.abs().max()) < 1e-12
+    empty = eng.new_acc()
+    fad.accumulate_clips(clips[:0], empty)
+    assert float(empty.abs().sum()) == 0.0
