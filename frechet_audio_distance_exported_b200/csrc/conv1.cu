@@ -57,9 +57,10 @@ __global__ void __launch_bounds__(256, 2) conv1_vggish_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------- CNN14: bn0 + conv + BN + ReLU
-// grid = (ceil(T / 4) row bands, B clips); block = 256 threads = 4 time rows x 64 mel columns, one pixel each;
-// output channels in 4 groups of 16 with warp-uniform (broadcast) weight loads, packed f32x2 FMAs.
-constexpr int kC14Rows = 4;
+// grid = (ceil(T / 16) row bands, B clips); block = 256 threads = 64 mel columns x 4 row groups; a thread owns
+// FOUR vertically adjacent pixels (rows 4q .. 4q+3 of the band) so every warp-uniform weight load feeds 4 x 8
+// packed FMAs (one pixel per thread left the loop dominated by loads and epilogue: 23 % of the FMA rate).
+constexpr int kC14Rows = 16;
 __global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __restrict__ feats, int T,
                                                              const float* __restrict__ bn0_scale,
                                                              const float* __restrict__ bn0_shift,
@@ -84,46 +85,56 @@ __global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __rest
     if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
 
-    const int ry = threadIdx.x >> 6;            // row within the band
+    const int q = threadIdx.x >> 6;             // row group: rows 4q .. 4q+3 of the band (warp-uniform)
     const int x = threadIdx.x & 63;
-    const int y = y0 + ry;
-    if (y >= T) return;
-    unsigned long long in[3][3];
+    unsigned long long in[6][3];                // 6 input rows x 3 columns, duplicated into f32x2
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float v = s_in[ry + r][x + c];
+            const float v = s_in[4 * q + r][x + c];
             in[r][c] = pack_f32x2(v, v);
         }
-    const size_t obase = ((size_t(clip) * T + y) * W + x) * 64;
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
-        unsigned long long acc[8];
+        unsigned long long acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0ull;
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][j] = 0ull;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(&s_w[ky * 3 + kx][g * 16]);   // warp-uniform
+                unsigned long long wv[8];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const ulonglong2 t = wp[v];
-                    acc[2 * v] = ffma2(in[ky][kx], t.x, acc[2 * v]);
-                    acc[2 * v + 1] = ffma2(in[ky][kx], t.y, acc[2 * v + 1]);
+                    wv[2 * v] = t.x;
+                    wv[2 * v + 1] = t.y;
                 }
-            }
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float a0, a1;
-            unpack_f32x2(acc[j], a0, a1);
-            const float2 bb = *reinterpret_cast<const float2*>(&s_b[g * 16 + 2 * j]);
-            v[2 * j] = fmaxf(a0 + bb.x, 0.f);
-            v[2 * j + 1] = fmaxf(a1 + bb.y, 0.f);
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[r][j] = ffma2(in[r + ky][kx], wv[j], acc[r][j]);
+            }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int y = y0 + 4 * q + r;
+            if (y < T) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a0, a1;
+                    unpack_f32x2(acc[r][j], a0, a1);
+                    const float2 bb = *reinterpret_cast<const float2*>(&s_b[g * 16 + 2 * j]);
+                    v[2 * j] = fmaxf(a0 + bb.x, 0.f);
+                    v[2 * j + 1] = fmaxf(a1 + bb.y, 0.f);
+                }
+                store16(v, out_hi, out_lo, ((size_t(clip) * T + y) * W + x) * 64 + g * 16);
+            }
         }
-        store16(v, out_hi, out_lo, obase + g * 16);
     }
 }
 

@@ -481,14 +481,13 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         // Thread = one accumulator row (pixel); a chunk = 32 output channels held in registers.
         // 2x2 pooling never leaves the warp: the tile box is at most 16 pixels wide, so a warp holds an
         // even number of complete tile rows and the 4 pixels of a pooling window are lanes
-        // {l, l^1, l^BW, l^BW^1} -> two shuffles per value, no shared-memory staging, no block barrier.
+        // {l, l^1, l^BW, l^BW^1} -> a shuffle butterfly, no shared-memory staging, no block barrier.
         const int ew = warp - 4;                     // TMEM lane quarter
         const int row = ew * 32 + lane;              // accumulator row (= pixel within the tile)
         const int ww = row % p.BW;
         const int t2 = row / p.BW;
         const int hh = t2 % p.BH;
         const int bb = t2 / p.BH;
-        const bool pool_lane = ((lane & 1) == 0) && ((lane & p.BW) == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -503,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             size_t obase;
             if (p.pool && !p.raw) {
                 const int px = x >> 1, py = y >> 1;
-                valid = pool_lane && px < p.Wo && py < p.Ho && b < p.B;
+                valid = px < p.Wo && py < p.Ho && b < p.B;          // all 4 lanes of a window store (8 channels each)
                 obase = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + n0;
             } else {
                 valid = x < p.W && y < p.H && b < p.B;
@@ -562,19 +561,49 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (p.pool == 1) {
+                if (p.pool) {
+                    // 2x2 pooling as a two-step butterfly that also SPLITS the channels: after exchanging with the
+                    // x-neighbour (lane ^ 1) the even lane owns pooled channels 0-15 and the odd lane 16-31; after
+                    // the y-neighbour (lane ^ BW) each of the 4 lanes of a window owns 8 pooled channels.
+                    // 24 shuffles per chunk instead of 64, and all 4 lanes take part in the store.
+                    const bool odd = (lane & 1) != 0;
+                    const bool up = (lane & p.BW) != 0;
+                    float hx[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], p.BW));
+                    for (int j = 0; j < 16; ++j) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[16 + j], 1);
+                        const float mine = odd ? v[16 + j] : v[j];
+                        hx[j] = p.pool == 1 ? fmaxf(mine, recv) : mine + recv;
                     }
-                } else if (p.pool == 2) {
+                    float g8[8];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
-                        v[j] += __shfl_xor_sync(0xffffffffu, v[j], p.BW);
-                        v[j] *= 0.25f;
+                    for (int j = 0; j < 8; ++j) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, up ? hx[j] : hx[8 + j], p.BW);
+                        const float mine = up ? hx[8 + j] : hx[j];
+                        g8[j] = p.pool == 1 ? fmaxf(mine, recv) : (mine + recv) * 0.25f;
                     }
+                    if (valid) {
+                        const size_t o = obase + c * 32 + (odd ? 16 : 0) + (up ? 8 : 0);
+                        if (p.out_f32) {
+                            float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
+                            d[0] = make_float4(g8[0], g8[1], g8[2], g8[3]);
+                            d[1] = make_float4(g8[4], g8[5], g8[6], g8[7]);
+                        } else {
+                            uint4 hi;
+                            hi.x = pack_bf16x2(g8[0], g8[1]); hi.y = pack_bf16x2(g8[2], g8[3]);
+                            hi.z = pack_bf16x2(g8[4], g8[5]); hi.w = pack_bf16x2(g8[6], g8[7]);
+                            *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
+                            if (p.out_lo) {
+                                uint4 lo;
+                                lo.x = pack_bf16x2(g8[0] - bf16_round(g8[0]), g8[1] - bf16_round(g8[1]));
+                                lo.y = pack_bf16x2(g8[2] - bf16_round(g8[2]), g8[3] - bf16_round(g8[3]));
+                                lo.z = pack_bf16x2(g8[4] - bf16_round(g8[4]), g8[5] - bf16_round(g8[5]));
+                                lo.w = pack_bf16x2(g8[6] - bf16_round(g8[6]), g8[7] - bf16_round(g8[7]));
+                                *reinterpret_cast<uint4*>(p.out_lo + o) = lo;
+                            }
+                        }
+                    }
+                    continue;
                 }
                 if (valid) {
                     const size_t o = obase + c * 32;
