@@ -16,12 +16,12 @@
 //     MMAs of tile i+1.
 //   * split-bf16 ("bf16x3") mode: the K loop runs three passes (A_hi*B_hi, A_lo*B_hi, A_hi*B_lo)
 //     into the same accumulator, giving ~2^-16 relative operand precision with the same kernel.
-//   * Epilogue (4 warps): tcgen05.ld -> +bias (folded BN) -> ReLU -> optional 2x2 max / avg pool done with
+//   * Epilogue (8 warps): tcgen05.ld -> +bias (folded BN) -> ReLU -> optional 2x2 max / avg pool done with
 //     two warp shuffles per value (the pooled layers use boxes <= 16 pixels wide, so a pooling window
 //     lives inside one warp) -> bf16 hi(/lo) or fp32 NHWC, 16-byte stores straight from registers.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = weight
+// producer in halo mode, warps 4..11 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter).
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -61,7 +61,7 @@ struct GemmParams {
     int* err_flag;
 };
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                     // 4 control warps + 8 epilogue warps
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // one 128-byte swizzle atom of bf16
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16384
@@ -260,6 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     const uint32_t bar_bfull = bar_bres + 8;                         // [8]  halo mode B ring
     const uint32_t bar_bempty = bar_bfull + 64;                      // [8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5 + 16);
+    // the layer's whole bias vector lives in shared memory (bars + 512 B): the epilogue reads it with broadcast
+    // LDS instead of exposing a global-load round trip per 32-column chunk (ncu: 16 % of all stall samples sat on
+    // the first FADD after the bias __ldg in the short-K layers)
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+    for (int i = threadIdx.x; i < p.N; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4);                        // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * s, 8);                        // one arrive per epilogue warp
         }
         mbar_init(bar_bres, 1);
         for (int s = 0; s < 8; ++s) {
@@ -482,7 +487,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         // 2x2 pooling never leaves the warp: the tile box is at most 16 pixels wide, so a warp holds an
         // even number of complete tile rows and the 4 pixels of a pooling window are lanes
         // {l, l^1, l^BW, l^BW^1} -> a shuffle butterfly, no shared-memory staging, no block barrier.
-        const int ew = warp - 4;                     // TMEM lane quarter
+        // 8 epilogue warps: two per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); the two
+        // warps of a quarter take alternate 32-column chunks, which doubles the epilogue rate of the short-K
+        // layers where the epilogue, not the MMA, sets the tile time.
+        const int ew = (warp - 4) & 3;               // TMEM lane quarter
+        const int grp = (warp - 4) >> 2;             // chunk parity handled by this warp
         const int row = ew * 32 + lane;              // accumulator row (= pixel within the tile)
         const int ww = row % p.BW;
         const int t2 = row / p.BW;
@@ -514,11 +523,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
 
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = grp; c < BN / 32; c += 2) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, r);
                 tmem_ld_wait();
-                if (c == BN / 32 - 1) {
+                if (c + 2 >= BN / 32) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
@@ -543,19 +552,16 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     }
                     continue;
                 }
-                if (p.bias) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+                {
+                    const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 bv = __ldg(bp + q);
+                        const float4 bv = bp[q];
                         v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bv.x;
                         v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bv.y;
                         v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bv.z;
                         v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bv.w;
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 }
                 if (p.relu) {
 #pragma unroll
@@ -867,7 +873,9 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         FADB_CUDA_CHECK(cudaEventCreate(&ev1));
         FADB_CUDA_CHECK(cudaEventRecord(ev0, st));
     }
-    const int budget = h->gemm_smem_budget;
+    const int bias_bytes = ((L.N * 4 + 127) / 128) * 128;
+    const int budget = h->gemm_smem_budget - bias_bytes;
+    FADB_REQUIRE(L.N <= 8192, "Cout=%d too large for the shared-memory bias vector", L.N);
     auto launch = [&](const GemmParams& q) {
         GemmParams pp = q;
         const int b_bytes = BN * kBlockK * 2;
@@ -879,12 +887,12 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                 pp.b_stages = 0;
                 pp.stages = (budget - res) / kHaloBytes;
                 if (pp.stages > 4) pp.stages = 4;
-                smem = res + pp.stages * kHaloBytes + GemmCfg<64>::kExtraBytes;
+                smem = res + pp.stages * kHaloBytes + GemmCfg<64>::kExtraBytes + bias_bytes;
             } else {
                 pp.b_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
                 pp.stages = (budget - pp.b_stages * b_bytes) / kHaloBytes;
                 if (pp.stages > 4) pp.stages = 4;
-                smem = pp.stages * kHaloBytes + pp.b_stages * b_bytes + GemmCfg<64>::kExtraBytes;
+                smem = pp.stages * kHaloBytes + pp.b_stages * b_bytes + GemmCfg<64>::kExtraBytes + bias_bytes;
             }
         } else {
             pp.halo = 0;
@@ -892,7 +900,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             pp.stages = budget / (kABytes + b_bytes);
             if (pp.stages > 8) pp.stages = 8;
             if (pp.stages < 2) pp.stages = 2;
-            smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes;
+            smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes + bias_bytes;
         }
         if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, smem, st>>>(pp);
         else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, smem, st>>>(pp);
