@@ -31,11 +31,13 @@ SYMBOLS = [
     ("fadb_embed_dim", C.c_int, [C.c_int]),
     ("fadb_embed", C.c_int, [_vp, _fp, _i64, _i64, _fp, _vp]),
     ("fadb_embed_pcm", C.c_int, [_vp, _fp, _i64, _i64, _i64, _fp, _vp]),
+    ("fadb_embed_pcm16", C.c_int, [_vp, _vp, _i64, _i64, _i64, _fp, _vp]),
     ("fadb_stats_accumulate", C.c_int, [_vp, _fp, _i64, C.c_int, _i64, _dp, _dp, _vp]),
     ("fadb_stats_accumulate_f64", C.c_int, [_vp, _dp, _i64, C.c_int, _i64, _dp, _dp, _vp]),
     ("fadb_stats_finalize", C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp, _vp]),
     ("fadb_frechet", C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_int, _dp, _vp]),
     ("fadb_fad_from_pcm_host", C.c_int, [_vp, _fp, _i64, _fp, _i64, _i64, _fp, _fp, C.POINTER(C.c_double)]),
+    ("fadb_fad_from_pcm16_host", C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _fp, _fp, C.POINTER(C.c_double)]),
     ("fadb_profile_enable", C.c_int, [_vp, C.c_int]),
     ("fadb_profile_read", C.c_int, [_vp, C.POINTER(C.c_double)]),
     ("fadb_launch_count", C.c_int64, [_vp]),

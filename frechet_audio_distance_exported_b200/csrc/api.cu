@@ -326,7 +326,7 @@ static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* 
 
 // PCM -> embeddings for VGGish, chunked.  (A side stream running front end + conv1 of chunk i+1 under the tcgen05
 // layers of chunk i was measured and gave no gain at any smem budget / stream priority; removed.)
-static int vggish_embed_pcm(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+static int vggish_embed_pcm(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                             int64_t rows, float* emb, cudaStream_t st) {
     const int d = 128;
     // the bf16x3 parity mode keeps raw fp32 partial sums of a whole layer: bound its batch to keep that scratch small
@@ -339,12 +339,12 @@ static int vggish_embed_pcm(fadb_handle* h, const float* pcm, int64_t n_clips, i
             // front end + conv1 in one kernel: the fp32 features never touch HBM
             FADB_CHECK(reserve_a1(h, 0));
             __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
-            FADB_CHECK(launch_vggish_front_conv1(h, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride, a1,
+            FADB_CHECK(launch_vggish_front_conv1(h, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride, a1,
                                                  a1_lo_plane(h, 0), st));
             FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0), nc * rows, emb + c0 * rows * d, st));
         } else {
             FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 96 * 64 * sizeof(float)));
-            FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm + c0 * pcm_stride, nc, n_samples, pcm_stride,
+            FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride,
                                        h->ws_feats.as<float>(), st));
             FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
         }
@@ -551,7 +551,7 @@ int fadb_frontend(fadb_handle* h, int model, const float* pcm_dev, int64_t n_cli
     const int64_t row_elems = (model == FADB_MODEL_VGGISH) ? 96 * 64 : 64;
     for (int64_t c0 = 0; c0 < n_clips; c0 += kMax) {
         const int64_t nc = (n_clips - c0 < kMax) ? n_clips - c0 : kMax;
-        FADB_CHECK(launch_frontend(h, model, pcm_dev + c0 * pcm_stride, nc, n_samples, pcm_stride,
+        FADB_CHECK(launch_frontend(h, model, PcmSrc{pcm_dev + c0 * pcm_stride, 0}, nc, n_samples, pcm_stride,
                                    feats_dev + c0 * rows * row_elems, (cudaStream_t)stream));
     }
     return FADB_OK;
@@ -582,10 +582,10 @@ int fadb_embed(fadb_handle* h, const float* feats_dev, int64_t n_items, int64_t 
     return check_device_flag(h);
 }
 
-int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
-                   float* emb_dev, void* stream) {
-    if (!h || !pcm_dev || !emb_dev) { set_error("fadb_embed_pcm: NULL argument"); return FADB_E_INVALID; }
-    if (!h->weights_ready) { set_error("fadb_embed_pcm: weights not committed"); return FADB_E_STATE; }
+static int embed_pcm_any(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                         float* emb_dev, void* stream, const char* who) {
+    if (!h || !pcm.ptr || !emb_dev) { set_error("%s: NULL argument", who); return FADB_E_INVALID; }
+    if (!h->weights_ready) { set_error("%s: weights not committed", who); return FADB_E_STATE; }
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int model = h->model;
@@ -593,18 +593,28 @@ int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_
     if (rows <= 0) return FADB_OK;       // clips too short: zero rows, like waveform_to_examples -> [0,1,96,64]
     const int d = embed_dim(model);
     if (model == FADB_MODEL_VGGISH) {
-        FADB_CHECK(vggish_embed_pcm(h, pcm_dev, n_clips, n_samples, pcm_stride, rows, emb_dev, st));
+        FADB_CHECK(vggish_embed_pcm(h, pcm, n_clips, n_samples, pcm_stride, rows, emb_dev, st));
     } else {
         const int64_t cpc = h->max_batch_cnn14;
         FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 64 * sizeof(float)));
         for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
             const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
-            FADB_CHECK(launch_frontend(h, model, pcm_dev + c0 * pcm_stride, nc, n_samples, pcm_stride,
+            FADB_CHECK(launch_frontend(h, model, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride,
                                        h->ws_feats.as<float>(), st));
             FADB_CHECK(cnn14_forward(h, h->ws_feats.as<float>(), nc, (int)rows, emb_dev + c0 * d, st));
         }
     }
     return check_device_flag(h);
+}
+
+int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                   float* emb_dev, void* stream) {
+    return embed_pcm_any(h, PcmSrc{pcm_dev, 0}, n_clips, n_samples, pcm_stride, emb_dev, stream, "fadb_embed_pcm");
+}
+
+int fadb_embed_pcm16(fadb_handle* h, const int16_t* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+                     float* emb_dev, void* stream) {
+    return embed_pcm_any(h, PcmSrc{pcm_dev, 1}, n_clips, n_samples, pcm_stride, emb_dev, stream, "fadb_embed_pcm16");
 }
 
 int fadb_stats_accumulate(fadb_handle* h, const float* emb_dev, int64_t n_rows, int d, int64_t row_stride,
@@ -635,9 +645,11 @@ int fadb_frechet(fadb_handle* h, const double* mu1_dev, const double* sigma1_dev
     return launch_frechet(h, mu1_dev, sigma1_dev, mu2_dev, sigma2_dev, d, out_dev, (cudaStream_t)stream);
 }
 
-int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_bg, const float* pcm_ev_host,
-                           int64_t n_ev, int64_t n_samples, float* emb_bg_host, float* emb_ev_host, double* fad_out) {
+static int fad_from_pcm_host_any(fadb_handle* h, const void* pcm_bg_host, int64_t n_bg, const void* pcm_ev_host,
+                                 int64_t n_ev, int64_t n_samples, int i16, float* emb_bg_host, float* emb_ev_host,
+                                 double* fad_out) {
     if (!h || !pcm_bg_host || !pcm_ev_host || !fad_out) { set_error("fadb_fad_from_pcm_host: NULL argument"); return FADB_E_INVALID; }
+    const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
     if (!h->weights_ready) { set_error("weights not committed"); return FADB_E_STATE; }
     cudaSetDevice(h->device);
     const int model = h->model;
@@ -653,8 +665,8 @@ int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_b
     double* mu[2] = {acc[1] + acc_n, acc[1] + acc_n + d};
     double* sg[2] = {mu[1] + d, mu[1] + d + (size_t)d * d};
     double* outd = sg[1] + (size_t)d * d;
-    FADB_CHECK(h->ws_pcm[0].reserve((size_t)cpc * n_samples * sizeof(float)));
-    FADB_CHECK(h->ws_pcm[1].reserve((size_t)cpc * n_samples * sizeof(float)));
+    FADB_CHECK(h->ws_pcm[0].reserve((size_t)cpc * n_samples * esz));
+    FADB_CHECK(h->ws_pcm[1].reserve((size_t)cpc * n_samples * esz));
     FADB_CHECK(h->ws_emb.reserve((size_t)cpc * rows * d * sizeof(float) * 2));
     cudaStream_t cs = h->copy_stream;
     cudaStream_t st = 0;   // legacy default stream orders against nothing else here; use a dedicated one
@@ -665,19 +677,19 @@ int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_b
     int buf = 0;
     int64_t chunk_idx = 0;
     for (int set = 0; set < 2; ++set) {
-        const float* src = set == 0 ? pcm_bg_host : pcm_ev_host;
+        const char* src = static_cast<const char*>(set == 0 ? pcm_bg_host : pcm_ev_host);
         float* emb_host = set == 0 ? emb_bg_host : emb_ev_host;
         const int64_t n = set == 0 ? n_bg : n_ev;
         for (int64_t c0 = 0; c0 < n; c0 += cpc, ++chunk_idx) {
             const int64_t nc = (n - c0 < cpc) ? n - c0 : cpc;
-            float* dpcm = h->ws_pcm[buf].as<float>();
+            void* dpcm = h->ws_pcm[buf].as<char>();
             float* demb = h->ws_emb.as<float>() + (size_t)buf * cpc * rows * d;
             if (chunk_idx >= 2) FADB_CUDA_CHECK(cudaStreamWaitEvent(cs, h->ev_compute[buf], 0));   // buffer free again
-            FADB_CUDA_CHECK(cudaMemcpyAsync(dpcm, src + c0 * n_samples, (size_t)nc * n_samples * sizeof(float),
+            FADB_CUDA_CHECK(cudaMemcpyAsync(dpcm, src + (size_t)c0 * n_samples * esz, (size_t)nc * n_samples * esz,
                                             cudaMemcpyHostToDevice, cs));
             FADB_CUDA_CHECK(cudaEventRecord(h->ev_copy[buf], cs));
             FADB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_copy[buf], 0));
-            FADB_CHECK(fadb_embed_pcm(h, dpcm, nc, n_samples, n_samples, demb, st));
+            FADB_CHECK(embed_pcm_any(h, PcmSrc{dpcm, i16}, nc, n_samples, n_samples, demb, st, "fadb_fad_from_pcm_host"));
             FADB_CHECK(launch_stats_accumulate(h, demb, nc * rows, d, d, nullptr, acc[set], st));
             if (emb_host)
                 FADB_CUDA_CHECK(cudaMemcpyAsync(emb_host + c0 * rows * d, demb, (size_t)nc * rows * d * sizeof(float),
@@ -695,10 +707,22 @@ int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_b
     return check_device_flag(h);
 }
 
+int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_bg, const float* pcm_ev_host,
+                           int64_t n_ev, int64_t n_samples, float* emb_bg_host, float* emb_ev_host, double* fad_out) {
+    return fad_from_pcm_host_any(h, pcm_bg_host, n_bg, pcm_ev_host, n_ev, n_samples, 0, emb_bg_host, emb_ev_host, fad_out);
+}
+
+int fadb_fad_from_pcm16_host(fadb_handle* h, const int16_t* pcm_bg_host, int64_t n_bg, const int16_t* pcm_ev_host,
+                             int64_t n_ev, int64_t n_samples, float* emb_bg_host, float* emb_ev_host, double* fad_out) {
+    return fad_from_pcm_host_any(h, pcm_bg_host, n_bg, pcm_ev_host, n_ev, n_samples, 1, emb_bg_host, emb_ev_host, fad_out);
+}
+
 int fadb_profile_enable(fadb_handle* h, int on) {
     if (!h) return FADB_E_INVALID;
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->prof_front) cudaEventDestroy(e);
     h->prof_events.clear();
+    h->prof_front.clear();
     h->prof_flops = 0.0;
     h->profile = on != 0;
     return FADB_OK;
@@ -717,7 +741,14 @@ int fadb_profile_read(fadb_handle* h, double* out4) {
     out4[0] = ms;
     out4[1] = h->prof_flops;
     out4[2] = (double)(h->prof_events.size() / 2);
-    out4[3] = 0.0;
+    double fms = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_front.size(); i += 2) {
+        FADB_CUDA_CHECK(cudaEventSynchronize(h->prof_front[i + 1]));
+        float t = 0.f;
+        FADB_CUDA_CHECK(cudaEventElapsedTime(&t, h->prof_front[i], h->prof_front[i + 1]));
+        fms += t;
+    }
+    out4[3] = fms;
     return FADB_OK;
 }
 

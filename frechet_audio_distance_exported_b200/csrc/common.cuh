@@ -126,7 +126,8 @@ struct fadb_handle {
     fadb::DevBuf ws_emb;        // embeddings of the host path
     // optional per-launch timing of the tensor-core layers (bench.py roofline leg)
     bool profile = false;
-    std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+    std::vector<cudaEvent_t> prof_events;   // pairs (start, stop) around tensor-core layer launches
+    std::vector<cudaEvent_t> prof_front;    // pairs (start, stop) around front-end (+ conv1) launches
     double prof_flops = 0.0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
@@ -136,11 +137,19 @@ struct fadb_handle {
 namespace fadb {
 
 // ---- kernels / launchers implemented across the .cu files ---------------------------------------
+// PCM source on the device: fp32 samples, or raw int16 PCM that the front end normalises by 1/32768 while loading
+// (the reference's dtype="int16" path, fad.py:145-149; exact in fp32, so both forms give identical features)
+struct PcmSrc {
+    const void* ptr;
+    int i16;
+    PcmSrc offset(int64_t samples) const { return PcmSrc{static_cast<const char*>(ptr) + samples * (i16 ? 2 : 4), i16}; }
+};
+
 // frontend.cu
-int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips, int64_t n_samples,
+int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int64_t n_samples,
                     int64_t pcm_stride, float* feats, cudaStream_t st);
 int frontend_init(fadb_handle* h);
-int launch_vggish_front_conv1(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                               __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
 
 int64_t frontend_rows(int model, int64_t n_samples);

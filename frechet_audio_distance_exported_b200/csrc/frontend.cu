@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "conv1_dev.cuh"
+#include "tc_ptx.cuh"
 
 namespace fadb {
 
@@ -36,7 +37,8 @@ struct FrontTables {
 static FrontTables g_tables[5];   // per model; built per process (device-global, read-only)
 
 struct FrontParams {
-    const float* pcm;
+    const void* pcm;    // fp32 samples, or int16 when pcm_i16
+    int pcm_i16;
     long long pcm_stride;
     int n_samples;      // samples physically present per clip
     int logical_len;    // length used for reflect padding (CLAP: 480000)
@@ -52,6 +54,21 @@ struct FrontParams {
     const float* band_wf;
     float* out;         // [n_clips][rows_out][64]
 };
+
+// one clip's samples: fp32, or int16 scaled by 2^-15 on load (exact)
+struct PcmView {
+    const float* f;
+    const short* s;
+    __device__ __forceinline__ float operator[](long long i) const {
+        return s ? (float)__ldg(s + i) * 3.0517578125e-05f : __ldg(f + i);
+    }
+};
+__device__ __forceinline__ PcmView clip_view(const void* base, int i16, long long clip, long long stride) {
+    PcmView v;
+    v.f = i16 ? nullptr : static_cast<const float*>(base) + clip * stride;
+    v.s = i16 ? static_cast<const short*>(base) + clip * stride : nullptr;
+    return v;
+}
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -69,24 +86,26 @@ __device__ __forceinline__ int pidx(int n) { return n + (n >> 3); }
 // (16-way bank conflicts at stride NF/64).
 template <int M>
 struct FftPlan {
-    // passes after the first (the first has all twiddles = 1)
-    static constexpr int kPasses = (M == 256) ? 3 : 4;                 // M=128: 4,4,2 ; M=256: 4,4,4 ; M=512: 4,4,4,2
-    static constexpr int radix(int i) { return (M == 256) ? 4 : (i == 2 + (M == 512) ? 2 : 4); }
+    // radix of every pass (the first pass has all twiddles = 1 and takes its input straight from the loader):
+    // M = 128: 4,4,4,2 ; M = 256: 8,8,4 ; M = 512: 8,8,8.  Radix 8 = one butterfly of 8 points per lane and pass:
+    // one shared-memory round trip less than radix 4 (ncu r01: this stage is shared-memory-wavefront bound).
+    static constexpr int kNumPasses = (M == 128) ? 4 : 3;
+    static constexpr int radix(int i) { return M == 128 ? (i == 3 ? 2 : 4) : (M == 256 ? (i == 2 ? 4 : 8) : 8); }
     static constexpr int per(int i) { return ((M / radix(i)) + 31) / 32; }
-    static constexpr int offset(int i) {                                // in units of 32 double2
+    static constexpr int offset(int i) {                                // twiddle slots before pass i >= 1, units of 32 double2
         int o = 0;
-        for (int j = 0; j < i; ++j) o += per(j) * (radix(j) - 1);
+        for (int j = 1; j < i; ++j) o += per(j) * (radix(j) - 1);
         return o;
     }
-    static constexpr int kSlots = offset(kPasses) * 32;                 // double2 entries
+    static constexpr int kSlots = offset(kNumPasses) * 32;              // double2 entries
 };
 
 template <int M, int NF>
 __device__ __forceinline__ void build_pass_twiddles(double2* __restrict__ ptw, const double2* __restrict__ tw_global) {
     using P = FftPlan<M>;
-    int pp = 4;
+    int pp = P::radix(0);
 #pragma unroll
-    for (int ps = 0; ps < P::kPasses; ++ps) {
+    for (int ps = 1; ps < P::kNumPasses; ++ps) {
         const int R = P::radix(ps), PER = P::per(ps), T = M / R;
         const int tstep = NF / (pp * R);
         for (int e = threadIdx.x; e < PER * (R - 1) * 32; e += blockDim.x) {
@@ -104,8 +123,10 @@ __device__ __forceinline__ void build_pass_twiddles(double2* __restrict__ ptw, c
 
 // One in-place Stockham pass of radix R over the warp's M-point buffer: every lane first pulls ALL of
 // its butterfly inputs into registers, the warp syncs, then the outputs go back to the same buffer.
-template <int M, int R, bool FIRST>
-__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ ptw, int pp, int lane) {
+// The FIRST pass takes its inputs from `load(n)` (windowed PCM straight from global memory) instead.
+template <int M, int R, bool FIRST, class Load>
+__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ ptw, int pp, int lane,
+                                         const Load& load) {
     constexpr int T = M / R;                 // butterflies in the pass
     constexpr int PER = (T + 31) / 32;       // per lane
     double2 u[PER][R];
@@ -115,8 +136,13 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
         if (T >= 32 || i < T) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                double2 v = x[pidx(i + r * T)];
-                if (!FIRST && r > 0) v = cmul(v, ptw[(q * (R - 1) + (r - 1)) * 32 + lane]);
+                double2 v;
+                if (FIRST) {
+                    v = load(i + r * T);
+                } else {
+                    v = x[pidx(i + r * T)];
+                    if (r > 0) v = cmul(v, ptw[(q * (R - 1) + (r - 1)) * 32 + lane]);
+                }
                 u[q][r] = v;
             }
         }
@@ -128,7 +154,27 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
         if (T >= 32 || i < T) {
             const int k = i & (pp - 1);
             const int j = (i - k) * R + k;
-            if (R == 4) {
+            if (R == 8) {
+                constexpr double kH = 0.70710678118654752440;
+                const double2 a0 = cadd(u[q][0], u[q][4]), a1 = csub(u[q][0], u[q][4]);
+                const double2 a2 = cadd(u[q][2], u[q][6]), t26 = csub(u[q][2], u[q][6]);
+                const double2 b0 = cadd(u[q][1], u[q][5]), b1 = csub(u[q][1], u[q][5]);
+                const double2 b2 = cadd(u[q][3], u[q][7]), t37 = csub(u[q][3], u[q][7]);
+                const double2 a3 = make_double2(t26.y, -t26.x), b3 = make_double2(t37.y, -t37.x);   // -i * (.)
+                const double2 e0 = cadd(a0, a2), e2 = csub(a0, a2), e1 = cadd(a1, a3), e3 = csub(a1, a3);
+                const double2 o0 = cadd(b0, b2), o2r = csub(b0, b2), o1r = cadd(b1, b3), o3r = csub(b1, b3);
+                const double2 o1 = make_double2(kH * (o1r.x + o1r.y), kH * (o1r.y - o1r.x));        // * (1 - i)/sqrt2
+                const double2 o2 = make_double2(o2r.y, -o2r.x);                                     // * -i
+                const double2 o3 = make_double2(kH * (o3r.y - o3r.x), -kH * (o3r.x + o3r.y));       // * (-1 - i)/sqrt2
+                x[pidx(j)] = cadd(e0, o0);
+                x[pidx(j + pp)] = cadd(e1, o1);
+                x[pidx(j + 2 * pp)] = cadd(e2, o2);
+                x[pidx(j + 3 * pp)] = cadd(e3, o3);
+                x[pidx(j + 4 * pp)] = csub(e0, o0);
+                x[pidx(j + 5 * pp)] = csub(e1, o1);
+                x[pidx(j + 6 * pp)] = csub(e2, o2);
+                x[pidx(j + 7 * pp)] = csub(e3, o3);
+            } else if (R == 4) {
                 const double2 v0 = cadd(u[q][0], u[q][2]);
                 const double2 v1 = csub(u[q][0], u[q][2]);
                 const double2 v2 = cadd(u[q][1], u[q][3]);
@@ -147,21 +193,16 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
     __syncwarp();
 }
 
-// complex FFT of length M (power of two, 128/256/512) as radix-4 passes (+ one radix-2 pass for odd log2)
-template <int M>
-__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ ptw, int lane) {
+// complex FFT of length M (128 / 256 / 512) of the sequence load(0..M-1), result in x (padded index pidx)
+template <int M, class Load>
+__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ ptw, int lane,
+                                            const Load& load) {
     using P = FftPlan<M>;
-    fft_pass<M, 4, true>(x, ptw, 1, lane);
-    fft_pass<M, 4, false>(x, ptw + P::offset(0) * 32, 4, lane);
-    fft_pass<M, 4, false>(x, ptw + P::offset(1) * 32, 16, lane);
-    if (M == 256) {
-        fft_pass<M, 4, false>(x, ptw + P::offset(2) * 32, 64, lane);
-    } else if (M == 128) {
-        fft_pass<M, 2, false>(x, ptw + P::offset(2) * 32, 64, lane);
-    } else {
-        fft_pass<M, 4, false>(x, ptw + P::offset(2) * 32, 64, lane);
-        fft_pass<M, 2, false>(x, ptw + P::offset(3) * 32, 256, lane);
-    }
+    constexpr int R0 = P::radix(0), R1 = P::radix(1), R2 = P::radix(2);
+    fft_pass<M, R0, true>(x, ptw, 1, lane, load);
+    fft_pass<M, R1, false>(x, ptw + P::offset(1) * 32, R0, lane, load);
+    fft_pass<M, R2, false>(x, ptw + P::offset(2) * 32, R0 * R1, lane, load);
+    if constexpr (P::kNumPasses == 4) fft_pass<M, P::radix(3), false>(x, ptw + P::offset(3) * 32, R0 * R1 * R2, lane, load);
 }
 
 constexpr int kFrontWarps = 8;
@@ -182,8 +223,8 @@ struct FrontSmem {
 
 // One STFT frame -> 64 log-mel values, by one warp.  out_row[lane] and out_row[lane + 32] are written
 // (global memory in the stand-alone kernel, the shared-memory patch tile in the fused VGGish kernel).
-template <int NF>
-__device__ __forceinline__ void frame_logmel(const FrontParams& p, const float* __restrict__ pcm, int row, int lane,
+template <int NF, bool SPLIT = false>
+__device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView pcm, int row, int lane,
                                              double2* __restrict__ x, float* __restrict__ spec,
                                              const double2* __restrict__ s_tw, const double* __restrict__ s_win,
                                              const double2* __restrict__ s_ptw, const int (&bst)[2], const int (&bln)[2],
@@ -192,14 +233,14 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const float* 
     // ---- load + window (fp32 PCM x fp64 Hann, like numpy's promotion): z[n] = x[2n] + i x[2n+1]
     const long long f0 = (long long)row * p.hop - (p.centered ? NF / 2 : 0);
     const bool interior = (f0 >= 0) && (f0 + p.win_len <= p.n_samples);
-#pragma unroll
-    for (int q = 0; q < M / 32; ++q) {
-        const int n = lane + 32 * q;
+    // the loader hands z[n] to the first FFT pass in registers: the windowed frame never makes its own round
+    // trip through shared memory
+    auto load_z = [&](int n) -> double2 {
         float s0 = 0.f, s1 = 0.f;
         if (2 * n < p.win_len) {
             if (interior) {
-                s0 = __ldg(pcm + f0 + 2 * n);
-                s1 = (2 * n + 1 < p.win_len) ? __ldg(pcm + f0 + 2 * n + 1) : 0.f;
+                s0 = pcm[f0 + 2 * n];
+                s1 = (2 * n + 1 < p.win_len) ? pcm[f0 + 2 * n + 1] : 0.f;
             } else {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -211,7 +252,7 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const float* 
                             if (src < 0) src = -src;
                             if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
                         }
-                        if (src >= 0 && src < p.n_samples) s = __ldg(pcm + src);
+                        if (src >= 0 && src < p.n_samples) s = pcm[src];
                     }
                     if (e == 0) s0 = s; else s1 = s;
                 }
@@ -222,11 +263,9 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const float* 
             }
         }
         const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * n]);
-        x[pidx(n)] = make_double2((double)s0 * wn.x, (double)s1 * wn.y);
-    }
-    __syncwarp();
-
-    fft_inplace<M>(x, s_ptw, lane);
+        return make_double2((double)s0 * wn.x, (double)s1 * wn.y);
+    };
+    fft_inplace<M>(x, s_ptw, lane, load_z);
 
     // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32
 #pragma unroll
@@ -253,7 +292,14 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const float* 
         float o;
         if (p.power_db) o = 10.0f * log10f(fmaxf(acc, 1e-10f));      // pann.py:133-134
         else o = logf(acc + 0.01f);                                  // vggish.py:227
-        out_row[lane + 32 * h2] = o;
+        if (SPLIT) {   // fused VGGish kernel: the tile holds {bf16 hi, bf16 lo} pairs, o = hi + lo to ~2^-17
+            const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(o - __bfloat162float(hi));
+            reinterpret_cast<uint32_t*>(out_row)[lane + 32 * h2] =
+                (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        } else {
+            out_row[lane + 32 * h2] = o;
+        }
     }
     __syncwarp();
 }
@@ -278,7 +324,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
     double2* x = s_buf + warp * S::kBufSlots;
     float* spec = s_spec + warp * S::kSpecPitch;
     const int clip = blockIdx.y;
-    const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
+    const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
     float* out = p.out + (size_t)clip * p.rows_out * 64;
     int bst[2], bln[2], bof[2];                      // this lane's two mel bands
 #pragma unroll
@@ -343,7 +389,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_k
     double2* x = s_buf + warp * S::kBufSlots;
     float* spec = s_spec + warp * S::kSpecPitch;
     const int clip = blockIdx.y, patch = blockIdx.x;
-    const float* pcm = p.pcm + (long long)clip * p.pcm_stride;
+    const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
     int bst[2], bln[2], bof[2];
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
@@ -373,6 +419,225 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_k
         }
         const size_t obase = ((pbase * 48 + prow) * 32 + lane) * 64;
         conv1_vggish_pixel(in, s_w, s_b, out_hi, out_lo, obase);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused VGGish kernel, tensor-core conv1.  Same phase 1; phase 2 runs conv3x3(1->64) as a tcgen05 GEMM:
+//   D[pixel, cout] = sum_k A[pixel, k] * B[cout, k],  K = 32 = 27 used columns:
+//     A = [x_hi(tap 0..7) | x_lo(tap 0..7) | x_hi(tap 0..7) | x_hi8, x_lo8, x_hi8, 0...]
+//     B = [w_hi(tap 0..7) | w_hi(tap 0..7) | w_lo(tap 0..7) | w_hi8, w_hi8, w_lo8, 0...]
+// i.e. the three significant terms of (x_hi + x_lo)(w_hi + w_lo) in ONE accumulation: conv1 keeps ~2^-17
+// operand precision in both precision modes at 2 MMAs (M=128, N=64, K=16) per 128 pixels.  Phase 1 leaves the
+// patch as {hi, lo} bf16 pairs, so building an A row is shared-memory words + byte permutes.
+// The 2x2 max pool costs no shuffles: a step covers 128 pooling WINDOWS (4 pooled rows) as FOUR M=128 tiles, one
+// per window position q = (dy, dx), accumulating into four TMEM column groups; TMEM lane = window, so a thread
+// reads the 4 candidates of its window from columns q*64 + ch and pools in registers.
+// A / B tiles are un-swizzled core-matrix tiles (tc_ptx.cuh make_nosw_desc); the A tiles overlay the FFT buffers,
+// which are idle in phase 2.  CTAs are persistent (tables, B tile, TMEM set up once) and loop over patches.
+// ------------------------------------------------------------------------------------------------
+struct FusedTcSmem {
+    using S = FrontSmem<512>;
+    static constexpr int kTilePitch = 80;                                     // words (8-byte aligned rows)
+    static constexpr int kTileBytes = 98 * kTilePitch * 4;
+    static constexpr int kATileBytes = 128 * 64;                              // 128 rows x K=32 bf16
+    static constexpr int kBBytes = 64 * 64;                                   // 64 couts x K=32 bf16
+    static constexpr int kBiasBytes = 64 * 4;
+    static constexpr int kCtlBytes = 32;                                      // mbarrier + TMEM slot
+    static constexpr uint32_t kLbo = 128;                                     // core matrix -> next one along K
+    static constexpr uint32_t kSbo = 512;                                     // 8-row group -> next one (4 K chunks each)
+    static constexpr int kTotal = S::kTotal + kTileBytes + kBBytes + kBiasBytes + kCtlBytes;
+    static_assert(4 * kATileBytes <= S::kBufBytes, "A tiles overlay the FFT buffers");
+};
+
+__global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_tc_kernel(
+    const FrontParams p, const float* __restrict__ conv_w, const float* __restrict__ conv_b, int patches_per_clip,
+    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, uint32_t desc_lbo,
+    uint32_t desc_sbo, int* err_flag, int dbg) {
+    constexpr int NF = 512, M = 256;
+    using S = FrontSmem<NF>;
+    using F = FusedTcSmem;
+    constexpr uint32_t lbo = F::kLbo, sbo = F::kSbo;
+    extern __shared__ __align__(16) uint8_t fsm[];
+    double2* s_tw = reinterpret_cast<double2*>(fsm);
+    double* s_win = reinterpret_cast<double*>(fsm + S::kTwBytes);
+    double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);
+    uint8_t* s_bufb = fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes;
+    double2* s_buf = reinterpret_cast<double2*>(s_bufb);
+    float* s_spec = reinterpret_cast<float*>(s_bufb + S::kBufBytes);
+    uint32_t (*s_tile)[F::kTilePitch] = reinterpret_cast<uint32_t (*)[F::kTilePitch]>(fsm + S::kTotal);
+    uint8_t* s_b = fsm + S::kTotal + F::kTileBytes;                                            // B operand tile
+    float* s_bias = reinterpret_cast<float*>(s_b + F::kBBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_b + F::kBBytes + F::kBiasBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
+    build_pass_twiddles<M, NF>(s_ptw, p.tw);
+    // zero halo: rows 0 and 97, columns 0 and 65 (tile row r holds frame r-1, column c holds mel c-1)
+    for (int i = threadIdx.x; i < 2 * F::kTilePitch; i += kFrontWarps * 32)
+        s_tile[(i / F::kTilePitch) * 97][i % F::kTilePitch] = 0u;
+    for (int i = threadIdx.x; i < 98; i += kFrontWarps * 32) { s_tile[i][0] = 0u; s_tile[i][65] = 0u; }
+    if (threadIdx.x < 64) s_bias[threadIdx.x] = conv_b[threadIdx.x];
+    {   // B operand: thread = (cout n, 16-byte chunk c); conv_w is [tap][cout] fp32
+        const int n = threadIdx.x >> 2, c = threadIdx.x & 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c < 3) {
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float f = __ldg(conv_w + j * 64 + n);
+                w[j] = (c == 2) ? f - bf16_round(f) : f;
+            }
+            v.x = pack_bf16x2(w[0], w[1]); v.y = pack_bf16x2(w[2], w[3]);
+            v.z = pack_bf16x2(w[4], w[5]); v.w = pack_bf16x2(w[6], w[7]);
+        } else {
+            const float f = __ldg(conv_w + 8 * 64 + n);
+            v.x = pack_bf16x2(f, f);
+            v.y = pack_bf16x2(f - bf16_round(f), 0.f);
+        }
+        *reinterpret_cast<uint4*>(s_b + (n >> 3) * sbo + c * lbo + (n & 7) * 16) = v;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);       // 4 window positions x 64 fp32 columns
+    fence_proxy_async();                                        // B tile (generic-proxy stores) -> visible to the MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    double2* x = s_buf + warp * S::kBufSlots;
+    float* spec = s_spec + warp * S::kSpecPitch;
+    int bst[2], bln[2], bof[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        bst[h2] = p.band_start[lane + 32 * h2];
+        bln[h2] = p.band_len[lane + 32 * h2];
+        bof[h2] = p.band_off[lane + 32 * h2];
+    }
+    // phase-2 roles: builder thread = (window w, dy), both dx; drain warp = (TMEM lane quarter, channel half)
+    const int bw = threadIdx.x & 127, bdy = threadIdx.x >> 7;
+    const uint32_t a_row_off = (uint32_t)(bw >> 3) * sbo + (uint32_t)(bw & 7) * 16;
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t a_base = smem_u32(s_bufb);
+    const uint64_t db = make_nosw_desc(smem_u32(s_b), desc_lbo, desc_sbo);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+#pragma unroll 1
+    for (int pi = blockIdx.x; pi < total_patches; pi += gridDim.x) {
+        const int clip = pi / patches_per_clip, patch = pi - clip * patches_per_clip;
+        const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
+        // ---- phase 1: 96 frames of this patch -> s_tile rows 1..96, columns 1..64 as {hi, lo} bf16 pairs
+        for (int fi = 0; fi < ((dbg & 1) ? 0 : 12); ++fi) {
+            const int fr = warp * 12 + fi;
+            frame_logmel<NF, true>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, bst, bln, bof,
+                                   reinterpret_cast<float*>(&s_tile[fr + 1][1]));
+        }
+        __syncthreads();
+
+        // ---- phase 2: conv1 + bias + ReLU + maxpool on the tensor core, 4 pooled rows per step
+#pragma unroll 1
+        for (int s = (dbg & 2) ? 12 : 0; s < 12; ++s) {
+            {
+                const int y = 2 * (4 * s + (bw >> 5)) + bdy;        // image row; tile row y + ky = image row y - 1 + ky
+                const int xx = 2 * (bw & 31);                        // image x of dx = 0; tile col xx + kx = image x - 1 + kx
+                uint32_t t[3][4];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint2 lo2 = *reinterpret_cast<const uint2*>(&s_tile[y + ky][xx]);
+                    const uint2 hi2 = *reinterpret_cast<const uint2*>(&s_tile[y + ky][xx + 2]);
+                    t[ky][0] = lo2.x; t[ky][1] = lo2.y; t[ky][2] = hi2.x; t[ky][3] = hi2.y;
+                }
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    uint32_t w[9];
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) w[ky * 3 + kx] = t[ky][dx + kx];
+                    uint4 hi4, lo4;
+                    hi4.x = __byte_perm(w[0], w[1], 0x5410); hi4.y = __byte_perm(w[2], w[3], 0x5410);
+                    hi4.z = __byte_perm(w[4], w[5], 0x5410); hi4.w = __byte_perm(w[6], w[7], 0x5410);
+                    lo4.x = __byte_perm(w[0], w[1], 0x7632); lo4.y = __byte_perm(w[2], w[3], 0x7632);
+                    lo4.z = __byte_perm(w[4], w[5], 0x7632); lo4.w = __byte_perm(w[6], w[7], 0x7632);
+                    uint8_t* arow = s_bufb + (bdy * 2 + dx) * F::kATileBytes + a_row_off;
+                    *reinterpret_cast<uint4*>(arow) = hi4;
+                    *reinterpret_cast<uint4*>(arow + lbo) = lo4;
+                    *reinterpret_cast<uint4*>(arow + 2 * lbo) = hi4;
+                    *reinterpret_cast<uint4*>(arow + 3 * lbo) = make_uint4(w[8], w[8] & 0xffffu, 0u, 0u);
+                }
+                fence_proxy_async();
+            }
+            tc_fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                if (elect_one()) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint64_t da = make_nosw_desc(a_base + q * F::kATileBytes, desc_lbo, desc_sbo);
+                        umma_bf16(tmem_base + q * 64, da, db, idesc, 0u);
+                        umma_bf16(tmem_base + q * 64, da + ((2 * lbo) >> 4), db + ((2 * lbo) >> 4), idesc, 1u);   // K 16..31
+                    }
+                    umma_commit(smem_u32(bar));
+                }
+                __syncwarp();
+            }
+            mbar_wait(smem_u32(bar), (uint32_t)s & 1u, err_flag);
+            tc_fence_after();
+            {
+                const int prow = 4 * s + quarter;
+                const size_t obase = (((size_t)pi * 48 + prow) * 32 + lane) * 64 + half * 32;
+                const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + half * 32;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    uint32_t r0[16], r1[16], r2[16], r3[16];
+                    tmem_ld_32x32b_x16(taddr + sub * 16, r0);
+                    tmem_ld_32x32b_x16(taddr + 64 + sub * 16, r1);
+                    tmem_ld_32x32b_x16(taddr + 128 + sub * 16, r2);
+                    tmem_ld_32x32b_x16(taddr + 192 + sub * 16, r3);
+                    tmem_ld_wait();
+                    float g[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {      // relu(max(.) + b) == max(relu(. + b))
+                        const float m = fmaxf(fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])),
+                                              fmaxf(__uint_as_float(r2[j]), __uint_as_float(r3[j])));
+                        g[j] = fmaxf(m + s_bias[half * 32 + sub * 16 + j], 0.f);
+                    }
+                    uint4 h0, h1;
+                    h0.x = pack_bf16x2(g[0], g[1]); h0.y = pack_bf16x2(g[2], g[3]);
+                    h0.z = pack_bf16x2(g[4], g[5]); h0.w = pack_bf16x2(g[6], g[7]);
+                    h1.x = pack_bf16x2(g[8], g[9]); h1.y = pack_bf16x2(g[10], g[11]);
+                    h1.z = pack_bf16x2(g[12], g[13]); h1.w = pack_bf16x2(g[14], g[15]);
+                    uint4* d = reinterpret_cast<uint4*>(out_hi + obase + sub * 16);
+                    d[0] = h0;
+                    d[1] = h1;
+                    if (out_lo) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) g[j] -= bf16_round(g[j]);
+                        h0.x = pack_bf16x2(g[0], g[1]); h0.y = pack_bf16x2(g[2], g[3]);
+                        h0.z = pack_bf16x2(g[4], g[5]); h0.w = pack_bf16x2(g[6], g[7]);
+                        h1.x = pack_bf16x2(g[8], g[9]); h1.y = pack_bf16x2(g[10], g[11]);
+                        h1.z = pack_bf16x2(g[12], g[13]); h1.w = pack_bf16x2(g[14], g[15]);
+                        uint4* e = reinterpret_cast<uint4*>(out_lo + obase + sub * 16);
+                        e[0] = h0;
+                        e[1] = h1;
+                    }
+                }
+            }
+            tc_fence_before();      // orders these TMEM reads before the next step's MMAs (via its __syncthreads)
+        }
+        __syncthreads();            // phase 1 of the next patch reuses the A-tile bytes and the patch tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -485,6 +750,8 @@ int frontend_init(fadb_handle* h) {
                                          front_smem<512>()));
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_frontend_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          front_smem<1024>()));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_vggish_front_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FusedTcSmem::kTotal));
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_vggish_front_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          FusedSmem::kTotal));
     return FADB_OK;
@@ -513,8 +780,26 @@ int64_t frontend_rows(int model, int64_t n) {
     }
 }
 
+
+// per-launch CUDA events of the front-end kernels when the profile hook is on (bench.py's front-end GB/s figure)
+struct FrontProfile {
+    fadb_handle* h;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    FrontProfile(fadb_handle* h_, cudaStream_t st_) : h(h_), st(st_) {
+        if (h->profile && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, st);
+    }
+    ~FrontProfile() {
+        if (e0 && e1) {
+            cudaEventRecord(e1, st);
+            h->prof_front.push_back(e0);
+            h->prof_front.push_back(e1);
+        }
+    }
+};
+
 // PCM -> conv1 output [n_clips * patches, 48, 32, 64] bf16 (hi / optional lo) in one kernel (VGGish only)
-int launch_vggish_front_conv1(fadb_handle* h, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
+int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                               __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
     FADB_CHECK(build_tables(FADB_MODEL_VGGISH));
     const FrontTables& t = g_tables[FADB_MODEL_VGGISH];
@@ -522,7 +807,7 @@ int launch_vggish_front_conv1(fadb_handle* h, const float* pcm, int64_t n_clips,
     if (n_clips <= 0 || patches <= 0) return FADB_OK;
     FADB_REQUIRE(n_clips <= 65535 && n_samples < (1LL << 30), "fused front end: clip count / length out of range");
     FrontParams p;
-    p.pcm = pcm; p.pcm_stride = pcm_stride;
+    p.pcm = pcm.ptr; p.pcm_i16 = pcm.i16; p.pcm_stride = pcm_stride;
     p.n_samples = (int)n_samples; p.logical_len = (int)n_samples;
     p.hop = t.hop; p.win_len = t.win_len;
     p.centered = 0; p.power_db = 0; p.quantize = 0;
@@ -532,14 +817,28 @@ int launch_vggish_front_conv1(fadb_handle* h, const float* pcm, int64_t n_clips,
     p.rows_out = (int)(patches * 96);
     p.frames_valid = p.rows_out;
     dim3 grid((unsigned)patches, (unsigned)n_clips);
-    fadb_vggish_front_conv1_kernel<<<grid, kFrontWarps * 32, FusedSmem::kTotal, st>>>(
-        p, h->conv1_w, h->conv1_b, (int)patches, out_hi, h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);
+    FrontProfile prof(h, st);
+    static const bool tc_conv1 = !(getenv("FADB_TC_CONV1") && atoi(getenv("FADB_TC_CONV1")) == 0);
+    static const int front_dbg = getenv("FADB_FRONT_DBG") ? atoi(getenv("FADB_FRONT_DBG")) : 0;            // bring-up only
+    static const bool desc_swap = getenv("FADB_C1_DESC_SWAP") && atoi(getenv("FADB_C1_DESC_SWAP")) != 0;   // bring-up only
+    __nv_bfloat16* lo = h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr;
+    if (tc_conv1) {
+        const int64_t total = patches * n_clips;
+        const int64_t slots = 2LL * h->sm_count;
+        fadb_vggish_front_conv1_tc_kernel<<<(unsigned)(total < slots ? total : slots), kFrontWarps * 32, FusedTcSmem::kTotal, st>>>(
+            p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo,
+            desc_swap ? FusedTcSmem::kSbo : FusedTcSmem::kLbo, desc_swap ? FusedTcSmem::kLbo : FusedTcSmem::kSbo, h->err_flag,
+            front_dbg);
+    }
+    else
+        fadb_vggish_front_conv1_kernel<<<grid, kFrontWarps * 32, FusedSmem::kTotal, st>>>(
+            p, h->conv1_w, h->conv1_b, (int)patches, out_hi, lo);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
 }
 
-int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips, int64_t n_samples,
+int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int64_t n_samples,
                     int64_t pcm_stride, float* feats, cudaStream_t st) {
     FADB_REQUIRE(model >= 0 && model <= 4, "unknown model %d", model);
     FADB_REQUIRE(n_samples > 0 && n_samples < (1LL << 30), "n_samples out of range");
@@ -547,7 +846,8 @@ int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips
     const FrontTables& t = g_tables[model];
     if (n_clips <= 0) return FADB_OK;
     FrontParams p;
-    p.pcm = pcm;
+    p.pcm = pcm.ptr;
+    p.pcm_i16 = pcm.i16;
     p.pcm_stride = pcm_stride;
     p.n_samples = (int)n_samples;
     p.logical_len = (int)n_samples;
@@ -576,6 +876,7 @@ int launch_frontend(fadb_handle* h, int model, const float* pcm, int64_t n_clips
     }
     FADB_REQUIRE(n_clips <= 65535, "front end: at most 65535 clips per call");
     dim3 grid((p.rows_out + 63) / 64, (unsigned)n_clips);
+    FrontProfile prof(h, st);
     if (t.nfft == 256) fadb_frontend_kernel<256><<<grid, 256, front_smem<256>(), st>>>(p);
     else if (t.nfft == 512) fadb_frontend_kernel<512><<<grid, 256, front_smem<512>(), st>>>(p);
     else fadb_frontend_kernel<1024><<<grid, 256, front_smem<1024>(), st>>>(p);

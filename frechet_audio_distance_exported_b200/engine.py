@@ -101,14 +101,15 @@ class Engine:
         return out
 
     def embed_pcm(self, pcm: torch.Tensor) -> torch.Tensor:
-        """pcm [n_clips, n_samples] fp32 cuda -> embeddings [rows, d] fp32 (front end + network)."""
-        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.dim() == 2 and pcm.stride(1) == 1
+        """pcm [n_clips, n_samples] cuda, fp32 in [-1, 1] or raw int16 PCM (scaled by 1/32768 in the front end)
+        -> embeddings [rows, d] fp32 (front end + network)."""
+        assert pcm.is_cuda and pcm.dtype in (torch.float32, torch.int16) and pcm.dim() == 2 and pcm.stride(1) == 1
         n_clips, n = pcm.shape
         rows = self.frontend_rows(n) if self.model_id == 0 else 1
         out = torch.empty((n_clips * max(rows, 0), self.dim), dtype=torch.float32, device=pcm.device)
         if out.numel():
-            check(self.lib.fadb_embed_pcm(self.h, _p(pcm), n_clips, n, pcm.stride(0), _p(out),
-                                          C.c_void_p(_stream_ptr())))
+            fn = self.lib.fadb_embed_pcm16 if pcm.dtype == torch.int16 else self.lib.fadb_embed_pcm
+            check(fn(self.h, _p(pcm), n_clips, n, pcm.stride(0), _p(out), C.c_void_p(_stream_ptr())))
         return out
 
     # ------------------------------------------------------------------ statistics
@@ -150,11 +151,11 @@ class Engine:
 
     # ------------------------------------------------------------------ whole path, host buffers
     def fad_from_pcm_host(self, pcm_bg: torch.Tensor, pcm_ev: torch.Tensor, return_embeddings: bool = False):
-        """pcm_* : [n_clips, n_samples] fp32 HOST tensors (pinned recommended).  One C call: chunked H2D
-        overlapped with compute, statistics, Frechet, scalar D2H."""
+        """pcm_* : [n_clips, n_samples] fp32 (or both raw int16 PCM) HOST tensors (pinned recommended).  One C call:
+        chunked H2D overlapped with compute, statistics, Frechet, scalar D2H."""
         for t in (pcm_bg, pcm_ev):
-            assert (not t.is_cuda) and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()
-        assert pcm_bg.shape[1] == pcm_ev.shape[1]
+            assert (not t.is_cuda) and t.dtype in (torch.float32, torch.int16) and t.dim() == 2 and t.is_contiguous()
+        assert pcm_bg.shape[1] == pcm_ev.shape[1] and pcm_bg.dtype == pcm_ev.dtype
         n = pcm_bg.shape[1]
         rows = self.frontend_rows(n) if self.model_id == 0 else 1
         eb = ee = None
@@ -162,8 +163,8 @@ class Engine:
             eb = torch.empty((pcm_bg.shape[0] * rows, self.dim), dtype=torch.float32).pin_memory()
             ee = torch.empty((pcm_ev.shape[0] * rows, self.dim), dtype=torch.float32).pin_memory()
         out = C.c_double(0.0)
-        check(self.lib.fadb_fad_from_pcm_host(self.h, _p(pcm_bg), pcm_bg.shape[0], _p(pcm_ev), pcm_ev.shape[0], n,
-                                              _p(eb), _p(ee), C.byref(out)))
+        fn = self.lib.fadb_fad_from_pcm16_host if pcm_bg.dtype == torch.int16 else self.lib.fadb_fad_from_pcm_host
+        check(fn(self.h, _p(pcm_bg), pcm_bg.shape[0], _p(pcm_ev), pcm_ev.shape[0], n, _p(eb), _p(ee), C.byref(out)))
         if return_embeddings:
             return out.value, eb.numpy(), ee.numpy()
         return out.value
@@ -175,6 +176,7 @@ class Engine:
         """-> (tensor-core layer ms, algorithmic FLOPs, launches) since profile_enable(True)."""
         out = (C.c_double * 4)()
         check(self.lib.fadb_profile_read(self.h, out))
+        self.front_ms = float(out[3])          # summed front-end (+ fused conv1) launch durations of the same window
         return float(out[0]), float(out[1]), int(out[2])
 
     def launch_count(self) -> int:

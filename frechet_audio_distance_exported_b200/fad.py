@@ -70,11 +70,16 @@ def _pad_to_clap_time(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def load_audio(fname: str, sample_rate: int, channels: int, dtype: str = "float32") -> np.ndarray:
-    """fad.py:133-161 for RIFF/WAV files (PCM 8/16/24/32-bit and IEEE float), without libsndfile."""
+def load_audio(fname: str, sample_rate: int, channels: int, dtype: str = "float32", raw_pcm16: bool = False) -> np.ndarray:
+    """fad.py:133-161 for RIFF/WAV files (PCM 8/16/24/32-bit and IEEE float), without libsndfile.
+    raw_pcm16=True (not in the reference): a mono 16-bit file already at `sample_rate` is returned as the raw
+    int16 samples; get_embeddings ships them to the GPU as they are and the front end applies the /32768 of
+    fad.py:148-149 there (same values, half the bytes)."""
     from scipy.io import wavfile
 
     sr, raw = wavfile.read(fname)
+    if raw_pcm16 and raw.dtype == np.int16 and raw.ndim == 1 and sr == sample_rate:
+        return raw
     if raw.dtype == np.uint8:
         f = (raw.astype(np.float64) - 128.0) / 128.0
     elif raw.dtype == np.int16:
@@ -198,11 +203,15 @@ class FrechetAudioDistance:
     # ------------------------------------------------------------------ fad.py:302-408
     def _prepare_clip(self, audio: np.ndarray, sr: int) -> np.ndarray:
         audio = np.asarray(audio)
+        raw16 = audio.dtype == np.int16 and audio.ndim == 1 and sr == self.sample_rate
+        if audio.dtype == np.int16 and not raw16:                              # raw PCM16 that needs host-side work first
+            audio = audio / 32768.0                                            # fad.py:148-149
         if audio.ndim > 1:                                                     # vggish.py:245-246 / pann.py:96-97
             audio = np.mean(audio, axis=1)
         if sr != self.sample_rate:                                             # vggish.py:249-250 / pann.py:100-101
             audio = resample(audio, sr, self.sample_rate)
-        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        # mono native-rate int16 PCM goes to the device as is (half the bytes); the front end divides by 32768
+        audio = np.ascontiguousarray(audio, dtype=np.int16 if raw16 else np.float32)
         if self.model_name == "clap" and audio.shape[0] > 480000:
             raise ValueError("CLAP clips are limited to 10 s")
         if self.model_name != "vggish" and self.model_name != "clap":
@@ -225,9 +234,9 @@ class FrechetAudioDistance:
         by_len: Dict[int, List[int]] = {}
         for i, a in enumerate(prepared):
             if a is not None:
-                by_len.setdefault(a.shape[0], []).append(i)
+                by_len.setdefault((a.shape[0], a.dtype.str), []).append(i)
         results: Dict[int, np.ndarray] = {}
-        for n, idxs in by_len.items():
+        for (n, _), idxs in by_len.items():
             try:
                 rows = self.engine.frontend_rows(n) if self.model_name == "vggish" else 1
                 if rows <= 0:
@@ -290,8 +299,8 @@ class FrechetAudioDistance:
         files = [f for f in os.listdir(dir) if not f.startswith(".")]
         if self.verbose:
             print(f"[Exported FAD] Loading audio from {dir}...")
-        tasks = [pool.apply_async(load_audio, args=(os.path.join(dir, f), self.sample_rate, self.channels, dtype))
-                 for f in files]
+        tasks = [pool.apply_async(load_audio, args=(os.path.join(dir, f), self.sample_rate, self.channels, dtype,
+                                                    dtype == "int16")) for f in files]
         pool.close()
         pool.join()
         return [t.get() for t in tasks]
@@ -335,7 +344,7 @@ class FrechetAudioDistance:
 
     # ------------------------------------------------------------------ B200 extensions
     def accumulate_clips(self, clips: torch.Tensor, acc: torch.Tensor, chunk_clips: int = 1024) -> None:
-        """Embed `clips` ([n, samples] fp32, HOST or device) and add their rows to the fp64 statistics
+        """Embed `clips` ([n, samples] fp32 or raw int16 PCM, HOST or device) and add their rows to the fp64 statistics
         buffer `acc`.  Host tensors are streamed in chunks through two device buffers on a copy
         stream so the host->device copy of chunk i+1 overlaps the kernels of chunk i (pin the host
         tensor for this to be asynchronous).  Embeddings never leave the GPU."""
@@ -344,12 +353,13 @@ class FrechetAudioDistance:
         if n == 0:
             return
         if clips.is_cuda:
-            eng.stats_accumulate(eng.embed_pcm(clips.to(torch.float32)), acc)
+            eng.stats_accumulate(eng.embed_pcm(clips if clips.dtype == torch.int16 else clips.to(torch.float32)), acc)
             return
-        assert clips.dtype == torch.float32 and clips.dim() == 2 and clips.is_contiguous()
+        assert clips.dtype in (torch.float32, torch.int16) and clips.dim() == 2 and clips.is_contiguous()
         chunk = min(chunk_clips, n)
-        if getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1]):
-            self._h2d_bufs = [torch.empty((chunk, clips.shape[1]), dtype=torch.float32, device=self.device)
+        if (getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1])
+                or self._h2d_bufs[0].dtype != clips.dtype):
+            self._h2d_bufs = [torch.empty((chunk, clips.shape[1]), dtype=clips.dtype, device=self.device)
                               for _ in range(2)]
             self._h2d_stream = torch.cuda.Stream()
             self._h2d_copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -369,7 +379,7 @@ class FrechetAudioDistance:
             self._h2d_done[b].record(cur)
 
     def score_clips(self, background: torch.Tensor, evalset: torch.Tensor) -> float:
-        """FAD of two in-memory clip sets ([n, samples] fp32, host or device).  With torch.distributed
+        """FAD of two in-memory clip sets ([n, samples] fp32 or raw int16 PCM, host or device).  With torch.distributed
         initialised each rank passes ITS shard (see dist.shard_bounds): it embeds the shard,
         accumulates {n, sum x, sum x x^T} in fp64, ONE all-reduce over `process_group`, then every
         rank finalises mean/covariance and the Frechet distance redundantly."""

@@ -102,6 +102,11 @@ int fadb_embed(fadb_handle* h, const float* feats_dev, int64_t n_items, int64_t 
  * VGGish, n_clips rows otherwise. */
 int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_t n_samples,
                    int64_t pcm_stride, float* emb_dev, void* stream);
+/* Same with raw 16-bit PCM (the WAV sample format; the reference's dtype="int16" path, fad.py:145-149): the
+ * front end scales by 1/32768 while loading, which is exact, so the result equals fadb_embed_pcm on
+ * float(pcm)/32768.  Halves the host->device and HBM bytes of the PCM.  pcm_stride in samples. */
+int fadb_embed_pcm16(fadb_handle* h, const int16_t* pcm_dev, int64_t n_clips, int64_t n_samples,
+                     int64_t pcm_stride, float* emb_dev, void* stream);
 
 /* ---------------------------------------------------------------- statistics
  * Replaces calculate_embd_statistics, fad.py:483-496, as a summable sufficient statistic.
@@ -135,11 +140,15 @@ int fadb_frechet(fadb_handle* h, const double* mu1_dev, const double* sigma1_dev
 int fadb_fad_from_pcm_host(fadb_handle* h, const float* pcm_bg_host, int64_t n_bg, const float* pcm_ev_host,
                            int64_t n_ev, int64_t n_samples, float* emb_bg_host, float* emb_ev_host,
                            double* fad_out);
+int fadb_fad_from_pcm16_host(fadb_handle* h, const int16_t* pcm_bg_host, int64_t n_bg, const int16_t* pcm_ev_host,
+                             int64_t n_ev, int64_t n_samples, float* emb_bg_host, float* emb_ev_host,
+                             double* fad_out);
 
 /* ---------------------------------------------------------------- introspection / tests */
 /* Per-launch CUDA-event timing of the tensor-core layers (for the roofline figure in bench.py):
  * enable(1) resets the counters; read() synchronises the recorded events and returns
- * out4 = { sum of layer launch durations in ms, algorithmic FLOPs of those launches, launches, 0 }. */
+ * out4 = { sum of layer launch durations in ms, algorithmic FLOPs of those launches, launches,
+ *          sum of front-end (+ fused conv1) launch durations in ms }. */
 int fadb_profile_enable(fadb_handle* h, int on);
 int fadb_profile_read(fadb_handle* h, double* out4);
 /* number of kernels this library has launched on this handle since creation */

@@ -121,6 +121,10 @@ def test_load_audio_wav(tmp_path):
     np.testing.assert_array_almost_equal(out2, a, decimal=4)
     out3 = load_audio(p, 16000, 1, dtype="int16")                                       # fad.py:148-149
     assert out3.dtype == np.float64 and np.abs(out3 - a).max() < 1e-4
+    raw = load_audio(p, 16000, 1, dtype="int16", raw_pcm16=True)                        # B200 extension: raw PCM16
+    assert raw.dtype == np.int16 and np.array_equal(raw / 32768.0, out3)
+    assert load_audio(p2, 16000, 1, dtype="int16", raw_pcm16=True).dtype == np.float64  # stereo: host path
+    assert load_audio(p, 8000, 1, dtype="int16", raw_pcm16=True).dtype == np.float64    # needs resampling: host path
     # resampling on load (reference tests/test_basic.py:212-228: 1 s at 44.1 kHz -> exactly 16000 samples)
     t = np.linspace(0, 1.0, 44100, dtype=np.float32)
     b = (np.sin(2 * np.pi * 440.0 * t) * 0.5).astype(np.float32)

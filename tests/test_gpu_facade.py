@@ -104,6 +104,8 @@ def test_score_directories_and_cache(tmp_path, fad_vgg):
                                    [int(f[:3]) for f in os.listdir(str(tmp_path / "ev")) if not f.startswith(".")]])
     assert len(names) == 5
     assert abs(s - ref) / abs(ref) < 5e-2                                  # bf16 mode, tiny rank-deficient sets
+    s16 = fad_vgg.score(str(tmp_path / "bg"), str(tmp_path / "ev"), dtype="int16")      # fad.py:145-149: raw PCM16 / 32768
+    assert s16 == s                                                        # same samples, half the bytes over PCIe
     assert fad_vgg.score(str(tmp_path / "empty_missing"), str(tmp_path / "ev")) == -1     # exception -> -1, fad.py:660-662
     os.makedirs(str(tmp_path / "empty"))
     assert fad_vgg.score(str(tmp_path / "empty"), str(tmp_path / "ev")) == -1             # fad.py:640-642

@@ -318,3 +318,45 @@ def test_host_streaming_multi_chunk_matches_single_call(vgg_sd):
     empty = eng.new_acc()
     fad.accumulate_clips(clips[:0], empty)
     assert float(empty.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("model,sr,n", [("vggish", 16000, 2 * 16000 + 400), ("pann-16k", 16000, 16000), ("clap", 48000, 48000)])
+def test_pcm16_ingest_equals_float_path(model, sr, n):
+    """Raw int16 PCM (the reference's dtype="int16" path, fad.py:145-149: sf.read int16, then / 32768.0) embeds to
+    exactly what the float path gives on int16 / 32768 — the scale is exact in fp32."""
+    from frechet_audio_distance_exported_b200 import Engine
+    sd = networks.vggish_random_state_dict(seed=0) if model == "vggish" else \
+        networks.cnn14_random_state_dict(seed=1, clap_head=(model == "clap"))
+    eng = Engine(model, sd)
+    f = np.stack([synth.eval_clip(i, n, sr) for i in range(3)])
+    q = np.round(f * 32767).astype(np.int16)
+    a = eng.embed_pcm(torch.from_numpy(q).cuda()).cpu().numpy()
+    b = eng.embed_pcm(torch.from_numpy((q.astype(np.float64) / 32768.0).astype(np.float32)).cuda()).cpu().numpy()
+    assert a.shape == b.shape and a.shape[0] > 0 and np.array_equal(a, b)
+    # strided rows (a view into a longer buffer): pcm_stride is in samples
+    wide = torch.zeros((3, n + 6), dtype=torch.int16, device="cuda")
+    wide[:, :n] = torch.from_numpy(q).cuda()
+    assert np.array_equal(eng.embed_pcm(wide[:, :n]).cpu().numpy(), a)
+
+
+def test_pcm16_host_paths(vgg_sd):
+    """int16 host buffers through the one-call C path and through score_clips == the float path on the same samples."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd)
+    eng = fad.engine
+    n = 2 * 16000 + 400
+    qb = np.round(np.stack([synth.background_clip(i, n) for i in range(9)]) * 32767).astype(np.int16)
+    qe = np.round(np.stack([synth.eval_clip(i, n, 16000) for i in range(7)]) * 32767).astype(np.int16)
+    fb = (qb.astype(np.float64) / 32768.0).astype(np.float32)
+    fe = (qe.astype(np.float64) / 32768.0).astype(np.float32)
+    ref = eng.fad_from_pcm_host(torch.from_numpy(fb), torch.from_numpy(fe))
+    got, eb, ee = eng.fad_from_pcm_host(torch.from_numpy(qb).pin_memory(), torch.from_numpy(qe).pin_memory(),
+                                        return_embeddings=True)
+    assert got == ref and eb.shape == (18, 128) and ee.shape == (14, 128)
+    s16 = fad.score_clips(torch.from_numpy(qb), torch.from_numpy(qe))
+    s32 = fad.score_clips(torch.from_numpy(fb), torch.from_numpy(fe))
+    assert s16 == s32 and abs(s16 - ref) / abs(ref) < 1e-9
+    # get_embeddings keeps mono native-rate int16 clips raw; mixed dtypes and lengths keep their order
+    out = fad.get_embeddings([qb[0], fb[1], qb[2][:16400]], 16000)
+    assert out.shape == (2 + 2 + 1, 128)
+    assert np.array_equal(out[:2], eb[:2]) and np.array_equal(out[2:4], eb[2:4])
