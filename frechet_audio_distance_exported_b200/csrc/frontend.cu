@@ -15,6 +15,7 @@
 // spectrum on (|X|, mel projection, log) fp32 is enough: sums of positives, relative error ~1e-7.
 // Real FFT of length NF = complex in-place Stockham FFT of length NF/2 (radix-4 passes + one radix-2
 // pass when needed, inputs of a pass staged in registers) + split.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -29,8 +30,8 @@ struct FrontTables {
     double* win = nullptr;     // [WIN] periodic Hann
     int* band_start = nullptr; // [64]
     int* band_len = nullptr;   // [64]
-    int* band_off = nullptr;   // [64]
-    float* band_w = nullptr;   // [sum len] fp32
+    float* band_wt = nullptr;  // [wt_rows][32] fp32: row (h2 ? wt_off1 : 0) + i, column lane = weight i of band lane + 32*h2
+    int wt_rows = 0, wt_off1 = 0;
     int nfft = 0, win_len = 0, hop = 0;
     bool ready = false;
 };
@@ -50,8 +51,8 @@ struct FrontParams {
     const double* win;
     const int* band_start;
     const int* band_len;
-    const int* band_off;
-    const float* band_wf;
+    const float* band_wt;   // transposed band weights (FrontTables::band_wt), staged in shared memory by the kernels
+    int wt_rows, wt_off1;
     float* out;         // [n_clips][rows_out][64]
 };
 
@@ -62,6 +63,22 @@ struct PcmView {
     __device__ __forceinline__ float operator[](long long i) const {
         return s ? (float)__ldg(s + i) * 3.0517578125e-05f : __ldg(f + i);
     }
+    // byte address of sample i (for prefetch instructions)
+    __device__ __forceinline__ const char* addr(long long i) const {
+        return s ? reinterpret_cast<const char*>(s + i) : reinterpret_cast<const char*>(f + i);
+    }
+    __device__ __forceinline__ int sample_bytes() const { return s ? 2 : 4; }
+    // samples i, i+1 in one load; valid when pair_aligned(i)
+    __device__ __forceinline__ bool pair_aligned(long long i) const {
+        return s ? ((reinterpret_cast<uintptr_t>(s + i) & 3) == 0) : ((reinterpret_cast<uintptr_t>(f + i) & 7) == 0);
+    }
+    __device__ __forceinline__ float2 pair(long long i) const {
+        if (s) {
+            const short2 v = __ldg(reinterpret_cast<const short2*>(s + i));
+            return make_float2((float)v.x * 3.0517578125e-05f, (float)v.y * 3.0517578125e-05f);
+        }
+        return __ldg(reinterpret_cast<const float2*>(f + i));
+    }
 };
 __device__ __forceinline__ PcmView clip_view(const void* base, int i16, long long clip, long long stride) {
     PcmView v;
@@ -69,6 +86,9 @@ __device__ __forceinline__ PcmView clip_view(const void* base, int i16, long lon
     v.s = i16 ? static_cast<const short*>(base) + clip * stride : nullptr;
     return v;
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -218,7 +238,9 @@ struct FrontSmem {
     static constexpr int kPtwBytes = FftPlan<M>::kSlots * 16;
     static constexpr int kBufBytes = kFrontWarps * kBufSlots * 16;
     static constexpr int kSpecBytes = kFrontWarps * kSpecPitch * 4;
-    static constexpr int kTotal = kTwBytes + kWinBytes + kPtwBytes + kBufBytes + kSpecBytes;
+    static constexpr int kWtRows = NF / 16;                               // >= band-weight rows of every model (checked on the host)
+    static constexpr int kWtBytes = kWtRows * 32 * 4;
+    static constexpr int kTotal = kTwBytes + kWinBytes + kPtwBytes + kBufBytes + kSpecBytes + kWtBytes;
 };
 
 // One STFT frame -> 64 log-mel values, by one warp.  out_row[lane] and out_row[lane + 32] are written
@@ -227,18 +249,29 @@ template <int NF, bool SPLIT = false>
 __device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView pcm, int row, int lane,
                                              double2* __restrict__ x, float* __restrict__ spec,
                                              const double2* __restrict__ s_tw, const double* __restrict__ s_win,
-                                             const double2* __restrict__ s_ptw, const int (&bst)[2], const int (&bln)[2],
-                                             const int (&bof)[2], float* __restrict__ out_row) {
+                                             const double2* __restrict__ s_ptw, const float* __restrict__ s_wt,
+                                             const int (&bst)[2], const int (&bln)[2], float* __restrict__ out_row) {
     constexpr int M = NF / 2;
     // ---- load + window (fp32 PCM x fp64 Hann, like numpy's promotion): z[n] = x[2n] + i x[2n+1]
     const long long f0 = (long long)row * p.hop - (p.centered ? NF / 2 : 0);
     const bool interior = (f0 >= 0) && (f0 + p.win_len <= p.n_samples);
+    // both samples of z[n] in one load when the pair is naturally aligned (8 B fp32 / 4 B int16) and inside the window
+    const bool pair_ok = interior && ((p.win_len & 1) == 0) && pcm.pair_aligned(f0);
+    {   // this warp's next frame (row + 1) starts one hop later: pull its lines into L1 while this frame computes
+        // (ncu r01: a third of all warp time in this phase was long-scoreboard stall on the PCM loads)
+        const long long nb = (f0 + p.hop) + (long long)lane * (128 / pcm.sample_bytes());
+        if (nb >= 0 && nb < (long long)p.n_samples && nb < f0 + p.hop + p.win_len + (128 / pcm.sample_bytes()))
+            prefetch_l1(pcm.addr(nb));
+    }
     // the loader hands z[n] to the first FFT pass in registers: the windowed frame never makes its own round
     // trip through shared memory
     auto load_z = [&](int n) -> double2 {
         float s0 = 0.f, s1 = 0.f;
         if (2 * n < p.win_len) {
-            if (interior) {
+            if (pair_ok) {
+                const float2 t = pcm.pair(f0 + 2 * n);
+                s0 = t.x; s1 = t.y;
+            } else if (interior) {
                 s0 = pcm[f0 + 2 * n];
                 s1 = (2 * n + 1 < p.win_len) ? pcm[f0 + 2 * n + 1] : 0.f;
             } else {
@@ -267,28 +300,36 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView
     };
     fft_inplace<M>(x, s_ptw, lane, load_z);
 
-    // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32
+    // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32.
+    // Bins k and M-k come from the same pair (Z[k], Z[M-k]): X[k] = ze + w_k zo, X[M-k] = conj(ze - w_k zo), so each
+    // lane reads a pair once and writes both bins (k = 0 gives DC and Nyquist, k = M/2 pairs with itself).
+    auto put = [&](int k, double re_d, double im_d) {
+        const float re = (float)re_d, im = (float)im_d;
+        const float pw = fmaf(re, re, im * im);
+        spec[k] = p.power_db ? pw : sqrtf(pw);
+    };
 #pragma unroll
-    for (int q = 0; q <= M / 32; ++q) {
+    for (int q = 0; q <= M / 64; ++q) {
         const int k = lane + 32 * q;
-        if (k <= M) {
-            const double2 a = x[pidx(k & (M - 1))];
+        if (k <= M / 2) {
+            const double2 a = x[pidx(k)];
             const double2 bz = x[pidx((M - k) & (M - 1))];
             const double2 ze = make_double2(0.5 * (a.x + bz.x), 0.5 * (a.y - bz.y));
             const double2 zo = make_double2(0.5 * (a.y + bz.y), -0.5 * (a.x - bz.x));   // (a - conj b) / (2i)
-            const double2 w = s_tw[k];                                                   // tw[M] = -1
-            const float re = (float)(ze.x + w.x * zo.x - w.y * zo.y);
-            const float im = (float)(ze.y + w.x * zo.y + w.y * zo.x);
-            const float pw = fmaf(re, re, im * im);
-            spec[k] = p.power_db ? pw : sqrtf(pw);
+            const double2 w = s_tw[k];
+            const double tx = w.x * zo.x - w.y * zo.y, ty = w.x * zo.y + w.y * zo.x;
+            put(k, ze.x + tx, ze.y + ty);
+            if (k != M / 2) put(M - k, ze.x - tx, ze.y - ty);
         }
     }
     __syncwarp();
-    // ---- mel projection (sparse triangular bands) + log, fp32
+    // ---- mel projection (sparse triangular bands) + log, fp32; weights transposed in shared memory (row i, column
+    // lane) so a warp's weight load is one conflict-free wavefront
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
         float acc = 0.f;
-        for (int i = 0; i < bln[h2]; ++i) acc = fmaf(__ldg(p.band_wf + bof[h2] + i), spec[bst[h2] + i], acc);
+        const float* wt = s_wt + (h2 ? p.wt_off1 : 0) * 32 + lane;
+        for (int i = 0; i < bln[h2]; ++i) acc = fmaf(wt[i * 32], spec[bst[h2] + i], acc);
         float o;
         if (p.power_db) o = 10.0f * log10f(fmaxf(acc, 1e-10f));      // pann.py:133-134
         else o = logf(acc + 0.01f);                                  // vggish.py:227
@@ -314,10 +355,12 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
     double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);          // per-pass twiddles
     double2* s_buf = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes);
     float* s_spec = reinterpret_cast<float*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes + S::kBufBytes);
+    float* s_wt = s_spec + S::kSpecBytes / 4;
 
     for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
     for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
     build_pass_twiddles<M, NF>(s_ptw, p.tw);
+    for (int i = threadIdx.x; i < p.wt_rows * 32; i += kFrontWarps * 32) s_wt[i] = p.band_wt[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -326,12 +369,11 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
     const int clip = blockIdx.y;
     const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
     float* out = p.out + (size_t)clip * p.rows_out * 64;
-    int bst[2], bln[2], bof[2];                      // this lane's two mel bands
+    int bst[2], bln[2];                      // this lane's two mel bands
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
         bst[h2] = p.band_start[lane + 32 * h2];
         bln[h2] = p.band_len[lane + 32 * h2];
-        bof[h2] = p.band_off[lane + 32 * h2];
     }
     for (int fi = 0; fi < kFramesPerWarp; ++fi) {
         const int row = blockIdx.x * (kFrontWarps * kFramesPerWarp) + warp * kFramesPerWarp + fi;
@@ -341,7 +383,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
             out[(size_t)row * 64 + lane + 32] = 0.f;
             continue;
         }
-        frame_logmel<NF>(p, pcm, row, lane, x, spec, s_tw, s_win, s_ptw, bst, bln, bof, out + (size_t)row * 64);
+        frame_logmel<NF>(p, pcm, row, lane, x, spec, s_tw, s_win, s_ptw, s_wt, bst, bln, out + (size_t)row * 64);
     }
 }
 
@@ -370,6 +412,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_k
     double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);
     double2* s_buf = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes);
     float* s_spec = reinterpret_cast<float*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes + S::kBufBytes);
+    float* s_wt = s_spec + S::kSpecBytes / 4;
     float (*s_tile)[FusedSmem::kTilePitch] = reinterpret_cast<float (*)[FusedSmem::kTilePitch]>(fsm + S::kTotal);
     float (*s_w)[64] = reinterpret_cast<float (*)[64]>(fsm + S::kTotal + FusedSmem::kTileBytes);
     float* s_b = reinterpret_cast<float*>(fsm + S::kTotal + FusedSmem::kTileBytes + 9 * 64 * 4);
@@ -377,6 +420,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_k
     for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
     for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
     build_pass_twiddles<M, NF>(s_ptw, p.tw);
+    for (int i = threadIdx.x; i < p.wt_rows * 32; i += kFrontWarps * 32) s_wt[i] = p.band_wt[i];
     for (int i = threadIdx.x; i < 9 * 64; i += kFrontWarps * 32) s_w[i / 64][i % 64] = conv_w[i];
     if (threadIdx.x < 64) s_b[threadIdx.x] = conv_b[threadIdx.x];
     // zero halo: rows 0 and 97, columns 0 and 65 (tile row r holds frame r-1, column c holds mel c-1)
@@ -390,17 +434,16 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_k
     float* spec = s_spec + warp * S::kSpecPitch;
     const int clip = blockIdx.y, patch = blockIdx.x;
     const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
-    int bst[2], bln[2], bof[2];
+    int bst[2], bln[2];
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
         bst[h2] = p.band_start[lane + 32 * h2];
         bln[h2] = p.band_len[lane + 32 * h2];
-        bof[h2] = p.band_off[lane + 32 * h2];
     }
     // ---- phase 1: 96 frames of this patch -> s_tile rows 1..96, columns 1..64
     for (int fi = 0; fi < 12; ++fi) {
         const int fr = warp * 12 + fi;
-        frame_logmel<NF>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, bst, bln, bof, &s_tile[fr + 1][1]);
+        frame_logmel<NF>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, s_wt, bst, bln, &s_tile[fr + 1][1]);
     }
     __syncthreads();
     // ---- phase 2: conv1 + ReLU + maxpool; thread = pooled pixel (warp = pooled row within a band of 8)
@@ -465,6 +508,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
     uint8_t* s_bufb = fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes;
     double2* s_buf = reinterpret_cast<double2*>(s_bufb);
     float* s_spec = reinterpret_cast<float*>(s_bufb + S::kBufBytes);
+    float* s_wt = s_spec + S::kSpecBytes / 4;
     uint32_t (*s_tile)[F::kTilePitch] = reinterpret_cast<uint32_t (*)[F::kTilePitch]>(fsm + S::kTotal);
     uint8_t* s_b = fsm + S::kTotal + F::kTileBytes;                                            // B operand tile
     float* s_bias = reinterpret_cast<float*>(s_b + F::kBBytes);
@@ -475,6 +519,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
     for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
     for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
     build_pass_twiddles<M, NF>(s_ptw, p.tw);
+    for (int i = threadIdx.x; i < p.wt_rows * 32; i += kFrontWarps * 32) s_wt[i] = p.band_wt[i];
     // zero halo: rows 0 and 97, columns 0 and 65 (tile row r holds frame r-1, column c holds mel c-1)
     for (int i = threadIdx.x; i < 2 * F::kTilePitch; i += kFrontWarps * 32)
         s_tile[(i / F::kTilePitch) * 97][i % F::kTilePitch] = 0u;
@@ -512,12 +557,11 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
 
     double2* x = s_buf + warp * S::kBufSlots;
     float* spec = s_spec + warp * S::kSpecPitch;
-    int bst[2], bln[2], bof[2];
+    int bst[2], bln[2];
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
         bst[h2] = p.band_start[lane + 32 * h2];
         bln[h2] = p.band_len[lane + 32 * h2];
-        bof[h2] = p.band_off[lane + 32 * h2];
     }
     // phase-2 roles: builder thread = (window w, dy), both dx; drain warp = (TMEM lane quarter, channel half)
     const int bw = threadIdx.x & 127, bdy = threadIdx.x >> 7;
@@ -531,10 +575,21 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
     for (int pi = blockIdx.x; pi < total_patches; pi += gridDim.x) {
         const int clip = pi / patches_per_clip, patch = pi - clip * patches_per_clip;
         const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
+        {   // start pulling the NEXT patch of this CTA (62 KB of PCM) into L2 now; it is read one patch period later
+            const int pn = pi + gridDim.x;
+            if (pn < total_patches) {
+                const int c2 = pn / patches_per_clip, p2 = pn - c2 * patches_per_clip;
+                const PcmView nx = clip_view(p.pcm, p.pcm_i16, c2, p.pcm_stride);
+                const long long first = (long long)p2 * 96 * p.hop, count = 95LL * p.hop + p.win_len;
+                const int per_line = 128 / nx.sample_bytes();
+                for (long long o = (long long)threadIdx.x * per_line; o < count; o += (long long)kFrontWarps * 32 * per_line)
+                    if (first + o < p.n_samples) prefetch_l2(nx.addr(first + o));
+            }
+        }
         // ---- phase 1: 96 frames of this patch -> s_tile rows 1..96, columns 1..64 as {hi, lo} bf16 pairs
         for (int fi = 0; fi < ((dbg & 1) ? 0 : 12); ++fi) {
             const int fr = warp * 12 + fi;
-            frame_logmel<NF, true>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, bst, bln, bof,
+            frame_logmel<NF, true>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, s_wt, bst, bln,
                                    reinterpret_cast<float*>(&s_tile[fr + 1][1]));
         }
         __syncthreads();
@@ -712,29 +767,33 @@ static int build_tables(int model) {
     std::vector<std::vector<double>> wc;
     if (model == FADB_MODEL_VGGISH) vggish_mel(t.nfft / 2 + 1, wc);
     else slaney_mel(sr, t.nfft, fmin, fmax, wc);
-    std::vector<int> bs(64), bl(64), bo(64);
-    std::vector<float> bw;
+    std::vector<int> bs(64), bl(64);
     for (int b = 0; b < 64; ++b) {
         int first = -1, last = -1;
         for (int k = 0; k < (int)wc[b].size(); ++k)
             if (wc[b][k] != 0.0) { if (first < 0) first = k; last = k; }
         if (first < 0) { first = 0; last = -1; }
-        bs[b] = first; bl[b] = last - first + 1; bo[b] = (int)bw.size();
-        for (int k = first; k <= last; ++k) bw.push_back((float)wc[b][k]);
+        bs[b] = first; bl[b] = last - first + 1;
     }
-    if (bw.empty()) bw.push_back(0.f);
+    // transposed weights: row (h2 ? max0 : 0) + i, column lane = weight i of band lane + 32*h2 (0 past the band's end)
+    int mx[2] = {0, 0};
+    for (int b = 0; b < 64; ++b) mx[b >> 5] = std::max(mx[b >> 5], bl[b]);
+    t.wt_off1 = mx[0];
+    t.wt_rows = std::max(mx[0] + mx[1], 1);
+    FADB_REQUIRE(t.wt_rows <= t.nfft / 16, "mel bands too wide for the shared-memory weight table (%d rows)", t.wt_rows);
+    std::vector<float> wt((size_t)t.wt_rows * 32, 0.f);
+    for (int b = 0; b < 64; ++b)
+        for (int i = 0; i < bl[b]; ++i) wt[(size_t)((b >> 5) * mx[0] + i) * 32 + (b & 31)] = (float)wc[b][bs[b] + i];
     FADB_CUDA_CHECK(cudaMalloc(&t.tw, tw.size() * sizeof(double2)));
     FADB_CUDA_CHECK(cudaMalloc(&t.win, win.size() * sizeof(double)));
     FADB_CUDA_CHECK(cudaMalloc(&t.band_start, 64 * sizeof(int)));
     FADB_CUDA_CHECK(cudaMalloc(&t.band_len, 64 * sizeof(int)));
-    FADB_CUDA_CHECK(cudaMalloc(&t.band_off, 64 * sizeof(int)));
-    FADB_CUDA_CHECK(cudaMalloc(&t.band_w, bw.size() * sizeof(float)));
+    FADB_CUDA_CHECK(cudaMalloc(&t.band_wt, wt.size() * sizeof(float)));
     FADB_CUDA_CHECK(cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.win, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.band_start, bs.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
     FADB_CUDA_CHECK(cudaMemcpy(t.band_len, bl.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
-    FADB_CUDA_CHECK(cudaMemcpy(t.band_off, bo.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
-    FADB_CUDA_CHECK(cudaMemcpy(t.band_w, bw.data(), bw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FADB_CUDA_CHECK(cudaMemcpy(t.band_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
     t.ready = true;
     return FADB_OK;
 }
@@ -812,7 +871,8 @@ int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64
     p.hop = t.hop; p.win_len = t.win_len;
     p.centered = 0; p.power_db = 0; p.quantize = 0;
     p.tw = t.tw; p.win = t.win;
-    p.band_start = t.band_start; p.band_len = t.band_len; p.band_off = t.band_off; p.band_wf = t.band_w;
+    p.band_start = t.band_start; p.band_len = t.band_len;
+    p.band_wt = t.band_wt; p.wt_rows = t.wt_rows; p.wt_off1 = t.wt_off1;
     p.out = nullptr;
     p.rows_out = (int)(patches * 96);
     p.frames_valid = p.rows_out;
@@ -857,7 +917,8 @@ int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int6
     p.power_db = (model != FADB_MODEL_VGGISH);
     p.quantize = (model == FADB_MODEL_CLAP);
     p.tw = t.tw; p.win = t.win;
-    p.band_start = t.band_start; p.band_len = t.band_len; p.band_off = t.band_off; p.band_wf = t.band_w;
+    p.band_start = t.band_start; p.band_len = t.band_len;
+    p.band_wt = t.band_wt; p.wt_rows = t.wt_rows; p.wt_off1 = t.wt_off1;
     p.out = feats;
     if (model == FADB_MODEL_VGGISH) {
         const int64_t patches = frontend_rows(model, n_samples);
