@@ -257,6 +257,7 @@ def run_b200(args):
     step_device()
     torch.cuda.synchronize()
     gemm_ms, gemm_flops, gemm_launches = eng.profile_read()
+    front_ms = eng.front_ms
     eng.profile_enable(False)
     peaks = _peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -264,13 +265,31 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("gemm_dram_bytes_per_launch")
+            tj = json.load(fh)
+        # measured DRAM bytes per patch over the 8 layer launches (ncu --set full, 4000-patch chunk), scaled to the
+        # patches the launches of this run process: average DRAM bytes per launch, like `achieved`
+        if tj.get("gemm_dram_bytes_per_patch") and gemm_launches:
+            traffic = tj["gemm_dram_bytes_per_patch"] * (2 * (hi - lo) * 10) / gemm_launches
+        else:
+            traffic = tj.get("gemm_dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
                 "kernel": "fadb_gemm_tc_kernel (tcgen05 implicit GEMM: 5 conv3x3 + 3 FC layers)",
                 "how": f"algorithmic 2*M*N*K FLOPs of {gemm_launches} launches / sum of their CUDA-event durations "
                        f"({gemm_ms:.2f} ms of a {ms_step:.2f} ms step); peak = {peaks['source']}",
                 "step_share": gemm_ms / ms_step if ms_step > 0 else None}
+
+    # ---- the front-end stage next to it (north_star: "reported as achieved HBM GB/s"): SURVEY 8d bytes per clip
+    # (640 000 B of PCM read + 245 760 B of fp32 patches); the fused kernel also runs conv1, so it writes the
+    # pooled conv1 activations (1 966 080 B per clip, bf16) instead of the patches
+    clips_step = 2 * (hi - lo)
+    frontend = {"bound": "hbm", "achieved": clips_step * 885760 / (front_ms * 1e-3) / 1e9 if front_ms > 0 else None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": clips_step * 885760 / (front_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if front_ms > 0 else None,
+                "kernel": "fadb_vggish_front_conv1_tc_kernel (fp64 FFT log-mel front end fused with tcgen05 conv1)",
+                "ms_per_step": front_ms, "step_share": front_ms / ms_step if ms_step > 0 else None,
+                "actual_bytes_per_clip": 640000 + 10 * 48 * 32 * 64 * 2,
+                "note": "bound by shared-memory wavefronts of the fp64 FFT and TMEM reads of conv1, not by HBM"}
 
     # ---- e2e through the public API from pinned host memory
     bg_h = torch.empty(bg.shape, dtype=torch.float32).pin_memory()
@@ -295,6 +314,29 @@ def run_b200(args):
     e2e = {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
            "api": "FrechetAudioDistance.score_clips(pinned_host_bg, pinned_host_ev)", "steps": e2e_steps,
            "fad": e2e_fad}
+
+    # ---- same job from raw 16-bit PCM (the WAV sample format; reference dtype="int16", fad.py:145-149): half the bytes
+    q = lambda t: (t * 32767.0).round_().to(torch.int16)
+    bg16 = torch.empty(bg.shape, dtype=torch.int16).pin_memory()
+    ev16 = torch.empty(ev.shape, dtype=torch.int16).pin_memory()
+    for src, dst in ((bg, bg16), (ev, ev16)):
+        for c0 in range(0, src.shape[0], 512):
+            dst[c0:c0 + 512].copy_(q(src[c0:c0 + 512].clone()))
+    torch.cuda.synchronize()
+    fad.score_clips(bg16, ev16)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e16_fad = fad.score_clips(bg16, ev16)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e16_s = torch.tensor([(t1 - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e16_s, op=dist.ReduceOp.MAX)
+    e2e_pcm16 = {"value": 2 * n_set / float(e16_s.item()), "unit": "clips/s",
+                 "h2d_bytes_per_step": int(bg16.numel() + ev16.numel()) * 2, "d2h_bytes_per_step": 8,
+                 "api": "FrechetAudioDistance.score_clips(pinned int16 PCM)", "steps": e2e_steps, "fad": e2e16_fad}
+    del bg16, ev16
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
@@ -324,7 +366,7 @@ def run_b200(args):
             "data": "synthetic (torch Philox on GPU, distributions of oracle/synth.py)",
             "config": workload_config(world, clips_per_set=args.clips_per_set),
             "fad": fad_value, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "frontend": frontend, "e2e_pcm16": e2e_pcm16, "cpu_baseline": cpu,
             "frac_of_tensor_roofline_whole_step": (value / world) * VGGISH_GFLOP_PER_CLIP / 1e3 / peaks["bf16_tflops"],
         }
         print(json.dumps(line))
