@@ -15,9 +15,9 @@
 // Everything is latency/L2-bound fp64 (the 33.5 MB matrix at d = 2048 is L2-resident):
 //   * Cholesky: blocked right-looking, NB = 64 (3 launches per panel)
 //   * two d^3 DGEMMs (CUDA-core DFMA, 64x64 tiles)
-//   * tridiagonalisation: ONE launch per Householder step — the rank-2 update of step k is fused with
-//     the symmetric matrix-vector product of step k+1, so the trailing matrix is read+written once
-//     per step; the O(d) vector algebra is recomputed by every CTA instead of synchronising the grid
+//   * tridiagonalisation: ONE persistent cooperative kernel, a grid-wide barrier per Householder step — the
+//     rank-2 update of step k is fused with the symmetric matrix-vector product of step k+1, so the trailing
+//     matrix is read+written once per step; the O(d) vector algebra is recomputed by every CTA
 //   * bisection: one thread per eigenvalue.
 #include <cooperative_groups.h>
 
@@ -257,7 +257,7 @@ __global__ void symmetrize_kernel(double* __restrict__ A, int d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Householder tridiagonalisation, one launch per step (k = -1 .. d-3)
+// Householder tridiagonalisation, one step (k = -1 .. d-3) per call of tridiag_step
 //   in : A (rows/cols >= k+1 current), v_k, beta_k, p_k = beta_k A v_k        (k = -1: all zero)
 //   out: A updated for rows/cols >= k+2, v_{k+1}, beta_{k+1}, p_{k+1}, diag[k+1], off[k+1]
 // vec layout: [v (d) | p (d) | beta (1)] , ping-pong by step parity.
