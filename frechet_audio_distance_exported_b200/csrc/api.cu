@@ -680,8 +680,10 @@ static int fad_from_pcm_host_any(fadb_handle* h, const void* pcm_bg_host, int64_
         const char* src = static_cast<const char*>(set == 0 ? pcm_bg_host : pcm_ev_host);
         float* emb_host = set == 0 ? emb_bg_host : emb_ev_host;
         const int64_t n = set == 0 ? n_bg : n_ev;
-        for (int64_t c0 = 0; c0 < n; c0 += cpc, ++chunk_idx) {
-            const int64_t nc = (n - c0 < cpc) ? n - c0 : cpc;
+        for (int64_t c0 = 0, step = 0; c0 < n; c0 += step, ++chunk_idx) {
+            // the very first chunk is a quarter of the rest: the kernels start after a quarter of a chunk's copy time
+            step = (chunk_idx == 0 && n > cpc && cpc >= 4) ? cpc / 4 : cpc;
+            const int64_t nc = (n - c0 < step) ? n - c0 : step;
             void* dpcm = h->ws_pcm[buf].as<char>();
             float* demb = h->ws_emb.as<float>() + (size_t)buf * cpc * rows * d;
             if (chunk_idx >= 2) FADB_CUDA_CHECK(cudaStreamWaitEvent(cs, h->ev_compute[buf], 0));   // buffer free again

@@ -154,6 +154,8 @@ int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int 
                        __nv_bfloat16* out_lo, cudaStream_t st) {
     if (n_clips <= 0) return FADB_OK;
     FADB_REQUIRE(n_clips <= 65535, "conv1: at most 65535 clips per batch");
+    // (a tcgen05 version of this kernel, like the fused VGGish one, measured the same 0.22 ms per 64 clips: the
+    // kernel is bound by writing its 8.45 MB of bf16 activations per clip to HBM, so the CUDA-core version stays)
     dim3 grid((unsigned)((T + kC14Rows - 1) / kC14Rows), (unsigned)n_clips);
     conv1_cnn14_kernel<<<grid, 256, 0, st>>>(feats, T, h->bn0_scale, h->bn0_shift, h->conv1_w, h->conv1_b, out_hi,
                                             h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);

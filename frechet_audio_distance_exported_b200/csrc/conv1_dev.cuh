@@ -94,4 +94,54 @@ __device__ __forceinline__ void conv1_vggish_pixel(const unsigned long long (&in
     }
 }
 
+// ---- conv1 as a tcgen05 GEMM (K = 32, see frontend.cu fadb_vggish_front_conv1_tc_kernel) --------------------------
+// Operand tiles are un-swizzled core-matrix tiles: element (row r, 16-byte K chunk c) at
+// (r >> 3) * kC1Sbo + c * kC1Lbo + (r & 7) * 16.
+constexpr uint32_t kC1Lbo = 128;                 // core matrix -> next one along K
+constexpr uint32_t kC1Sbo = 512;                 // 8-row group -> next one (4 K chunks each)
+constexpr int kC1ATileBytes = 128 * 64;          // 128 pixels x K=32 bf16
+constexpr int kC1BBytes = 64 * 64;               // 64 couts x K=32 bf16
+
+// {bf16 hi, bf16 lo} of x packed in one word (hi in the low half), x = hi + lo to ~2^-17
+__device__ __forceinline__ uint32_t split_hi_lo(float x) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
+// B operand [64 couts][K=32] = [w_hi(tap 0..7) | w_hi(tap 0..7) | w_lo(tap 0..7) | w_hi8, w_hi8, w_lo8, 0...];
+// conv_w is [tap][cout] fp32; call with tid = 0..255 (thread = cout n, chunk c)
+__device__ __forceinline__ void c1tc_build_b(uint8_t* s_b, const float* __restrict__ conv_w, int tid) {
+    const int n = tid >> 2, c = tid & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c < 3) {
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float f = __ldg(conv_w + j * 64 + n);
+            w[j] = (c == 2) ? f - bfr(f) : f;
+        }
+        v.x = pack2(w[0], w[1]); v.y = pack2(w[2], w[3]); v.z = pack2(w[4], w[5]); v.w = pack2(w[6], w[7]);
+    } else {
+        const float f = __ldg(conv_w + 8 * 64 + n);
+        v.x = pack2(f, f);
+        v.y = pack2(f - bfr(f), 0.f);
+    }
+    *reinterpret_cast<uint4*>(s_b + (n >> 3) * kC1Sbo + c * kC1Lbo + (n & 7) * 16) = v;
+}
+
+// A row = [x_hi(tap 0..7) | x_lo(tap 0..7) | x_hi(tap 0..7) | x_hi8, x_lo8, x_hi8, 0...] from the 9 {hi, lo} words
+// of a pixel's 3x3 window; arow = address of the row's chunk 0
+__device__ __forceinline__ void c1tc_store_a_row(uint8_t* arow, const uint32_t (&w)[9]) {
+    uint4 hi4, lo4;
+    hi4.x = __byte_perm(w[0], w[1], 0x5410); hi4.y = __byte_perm(w[2], w[3], 0x5410);
+    hi4.z = __byte_perm(w[4], w[5], 0x5410); hi4.w = __byte_perm(w[6], w[7], 0x5410);
+    lo4.x = __byte_perm(w[0], w[1], 0x7632); lo4.y = __byte_perm(w[2], w[3], 0x7632);
+    lo4.z = __byte_perm(w[4], w[5], 0x7632); lo4.w = __byte_perm(w[6], w[7], 0x7632);
+    *reinterpret_cast<uint4*>(arow) = hi4;
+    *reinterpret_cast<uint4*>(arow + kC1Lbo) = lo4;
+    *reinterpret_cast<uint4*>(arow + 2 * kC1Lbo) = hi4;
+    *reinterpret_cast<uint4*>(arow + 3 * kC1Lbo) = make_uint4(w[8], w[8] & 0xffffu, 0u, 0u);
+}
+
 }  // namespace fadb

@@ -483,12 +483,11 @@ struct FusedTcSmem {
     using S = FrontSmem<512>;
     static constexpr int kTilePitch = 80;                                     // words (8-byte aligned rows)
     static constexpr int kTileBytes = 98 * kTilePitch * 4;
-    static constexpr int kATileBytes = 128 * 64;                              // 128 rows x K=32 bf16
-    static constexpr int kBBytes = 64 * 64;                                   // 64 couts x K=32 bf16
+    static constexpr int kATileBytes = kC1ATileBytes;                         // 128 rows x K=32 bf16
+    static constexpr int kBBytes = kC1BBytes;                                 // 64 couts x K=32 bf16
     static constexpr int kBiasBytes = 64 * 4;
     static constexpr int kCtlBytes = 32;                                      // mbarrier + TMEM slot
-    static constexpr uint32_t kLbo = 128;                                     // core matrix -> next one along K
-    static constexpr uint32_t kSbo = 512;                                     // 8-row group -> next one (4 K chunks each)
+    static constexpr uint32_t kLbo = kC1Lbo, kSbo = kC1Sbo;                   // operand tile layout of conv1_dev.cuh
     static constexpr int kTotal = S::kTotal + kTileBytes + kBBytes + kBiasBytes + kCtlBytes;
     static_assert(4 * kATileBytes <= S::kBufBytes, "A tiles overlay the FFT buffers");
 };
@@ -525,25 +524,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
         s_tile[(i / F::kTilePitch) * 97][i % F::kTilePitch] = 0u;
     for (int i = threadIdx.x; i < 98; i += kFrontWarps * 32) { s_tile[i][0] = 0u; s_tile[i][65] = 0u; }
     if (threadIdx.x < 64) s_bias[threadIdx.x] = conv_b[threadIdx.x];
-    {   // B operand: thread = (cout n, 16-byte chunk c); conv_w is [tap][cout] fp32
-        const int n = threadIdx.x >> 2, c = threadIdx.x & 3;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (c < 3) {
-            float w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float f = __ldg(conv_w + j * 64 + n);
-                w[j] = (c == 2) ? f - bf16_round(f) : f;
-            }
-            v.x = pack_bf16x2(w[0], w[1]); v.y = pack_bf16x2(w[2], w[3]);
-            v.z = pack_bf16x2(w[4], w[5]); v.w = pack_bf16x2(w[6], w[7]);
-        } else {
-            const float f = __ldg(conv_w + 8 * 64 + n);
-            v.x = pack_bf16x2(f, f);
-            v.y = pack_bf16x2(f - bf16_round(f), 0.f);
-        }
-        *reinterpret_cast<uint4*>(s_b + (n >> 3) * sbo + c * lbo + (n & 7) * 16) = v;
-    }
+    c1tc_build_b(s_b, conv_w, threadIdx.x);              // B operand [64 couts][K=32] (conv1_dev.cuh)
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(bar), 1);
         fence_barrier_init();
@@ -614,16 +595,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) w[ky * 3 + kx] = t[ky][dx + kx];
-                    uint4 hi4, lo4;
-                    hi4.x = __byte_perm(w[0], w[1], 0x5410); hi4.y = __byte_perm(w[2], w[3], 0x5410);
-                    hi4.z = __byte_perm(w[4], w[5], 0x5410); hi4.w = __byte_perm(w[6], w[7], 0x5410);
-                    lo4.x = __byte_perm(w[0], w[1], 0x7632); lo4.y = __byte_perm(w[2], w[3], 0x7632);
-                    lo4.z = __byte_perm(w[4], w[5], 0x7632); lo4.w = __byte_perm(w[6], w[7], 0x7632);
-                    uint8_t* arow = s_bufb + (bdy * 2 + dx) * F::kATileBytes + a_row_off;
-                    *reinterpret_cast<uint4*>(arow) = hi4;
-                    *reinterpret_cast<uint4*>(arow + lbo) = lo4;
-                    *reinterpret_cast<uint4*>(arow + 2 * lbo) = hi4;
-                    *reinterpret_cast<uint4*>(arow + 3 * lbo) = make_uint4(w[8], w[8] & 0xffffu, 0u, 0u);
+                    c1tc_store_a_row(s_bufb + (bdy * 2 + dx) * F::kATileBytes + a_row_off, w);
                 }
                 fence_proxy_async();
             }

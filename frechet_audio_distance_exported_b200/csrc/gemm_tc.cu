@@ -37,7 +37,7 @@ namespace fadb {
 struct GemmParams {
     CUtensorMap tmA[2];   // activations hi, lo : dims (C, W, H, B)
     CUtensorMap tmB[2];   // weights hi, lo     : dims (Ktot, N)
-    CUtensorMap tmH;      // halo mode: activations hi with box (64 ch, 16 px, 18 rows, 1 image)
+    CUtensorMap tmH;      // halo mode: activations hi with box (64 ch, 10 px, 18 rows, 1 image)
     int W, H, B;
     int BW, BH, BB;       // box; BW*BH*BB == 128
     int tiles_w, tiles_h, tiles_b, tiles_n;
@@ -66,7 +66,9 @@ constexpr int kThreads = 384;                     // 4 control warps + 8 epilogu
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // one 128-byte swizzle atom of bf16
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16384
-constexpr int kHaloBytes = 18 * 16 * 128;         // halo tile: 18 rows x 16 pixels x 64 channels bf16 = 36864
+constexpr int kHaloW = 10;                        // halo tile: (8 + 2) pixels x 18 rows x 64 channels bf16
+constexpr int kHaloBoxBytes = 18 * kHaloW * 128;  // 23040 B land per TMA box
+constexpr int kHaloBytes = (kHaloBoxBytes + 1023) / 1024 * 1024;   // stage pitch: keeps every stage 1024-B aligned
 
 template <int BN>
 struct GemmCfg {
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)kHaloBytes);
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)kHaloBoxBytes);
                         tma_load_4d(&p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes, cb * kBlockK,
                                     wt * p.BW - 1, ht * p.BH - 1, bt);
                     }
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     if (elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            const uint64_t da = da0 + (uint64_t)(((tap / 3) * 16 + (tap % 3)) * 8);   // (ky*16+kx)*128 B >> 4
+                            const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
                             const uint64_t db = db0 + (uint64_t)(tap * bstep);
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k)
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
                         tc_fence_after();
-                        const uint64_t da = da0 + (uint64_t)(((tap / 3) * 16 + (tap % 3)) * 8);
+                        const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);
                         const uint64_t db = make_sw128_desc(bring_base + bs * Cfg::kBBytes);
                         if (elect_one()) {
 #pragma unroll
@@ -640,7 +642,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
 
     // halo mode (single-pass 3x3 layers on maps at least 8 wide / 16 high): 8 x 16 pixel tiles whose input is ONE
-    // 18 x 16-pixel halo box per channel block instead of nine shifted boxes -> 4x less L2 -> SM traffic for
+    // 10 x 18-pixel halo box per channel block instead of nine shifted boxes -> 6x less L2 -> SM traffic for
     // the A operand.  Only used when H is large against the 16-row tile (few wasted rows).
     int halo = 0;
     int BW = 1, BH = 1, BB = 1;
@@ -682,7 +684,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     GemmParams p;
     memset(&p, 0, sizeof(p));
     FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB));
-    if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, 16, 18, 1));
+    if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1));
     else p.tmH = p.tmA[0];
     p.halo = halo;
     FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN));

@@ -146,17 +146,17 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Halo mode: the A operand of tap (dy, dx) is a VIEW into one shared-memory halo tile of 18 rows x 16 pixels
+// Halo mode: the A operand of tap (dy, dx) is a VIEW into one shared-memory halo tile of 18 rows x 10 pixels
 // x 128 B.  An accumulator row group (8 pixels of one image row) is 8 consecutive 128-B rows of the halo tile;
-// consecutive groups are one halo row (2048 B) apart -> SBO = 2048.  The view starts dx rows into a 1024-B
-// swizzle atom; measured on B200: the 128-B swizzle is applied to ABSOLUTE shared-memory address bits (the same
-// bits TMA used when it wrote the tile), so the descriptor's base-offset field must stay 0 — setting it to the
-// row phase gives wrong results.
+// consecutive groups are one halo row (1280 B) apart -> SBO = 1280.  The view starts (dy*10 + dx) rows into the
+// tile, so neither the start nor the groups sit on 1024-B swizzle-atom boundaries; measured on B200: the 128-B
+// swizzle is applied to ABSOLUTE shared-memory address bits (the same bits TMA used when it wrote the tile), so
+// the descriptor's base-offset field must stay 0 — setting it to the row phase gives wrong results.
 __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>(2048 >> 4) << 32;
+    d |= static_cast<uint64_t>(1280 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;
     return d;

@@ -357,6 +357,7 @@ class FrechetAudioDistance:
             return
         assert clips.dtype in (torch.float32, torch.int16) and clips.dim() == 2 and clips.is_contiguous()
         chunk = min(chunk_clips, n)
+        cur = torch.cuda.current_stream()
         if (getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1])
                 or self._h2d_bufs[0].dtype != clips.dtype):
             self._h2d_bufs = [torch.empty((chunk, clips.shape[1]), dtype=clips.dtype, device=self.device)
@@ -364,14 +365,22 @@ class FrechetAudioDistance:
             self._h2d_stream = torch.cuda.Stream()
             self._h2d_copied = [torch.cuda.Event(), torch.cuda.Event()]
             self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-        cur = torch.cuda.current_stream()
-        self._h2d_stream.wait_stream(cur)
-        for i, c0 in enumerate(range(0, n, chunk)):
-            b = i & 1
-            nc = min(chunk, n - c0)
+            self._h2d_next = 0
+            self._h2d_stream.wait_stream(cur)                  # fresh buffers: order after whatever ran before
+        # The copy stream only ever waits for the kernels that last READ the buffer it is about to overwrite
+        # (events persist across calls), so the first copy of a set overlaps the tail of the previous set; the
+        # first chunk of a call is small, so the kernels start after a quarter of a chunk's copy time.
+        bounds, c0 = [], 0
+        first = max(1, chunk // 4) if n > chunk else chunk
+        while c0 < n:
+            nc = min(first if c0 == 0 else chunk, n - c0)
+            bounds.append((c0, nc))
+            c0 += nc
+        for c0, nc in bounds:
+            b = self._h2d_next
+            self._h2d_next ^= 1
             with torch.cuda.stream(self._h2d_stream):
-                if i >= 2:
-                    self._h2d_stream.wait_event(self._h2d_done[b])
+                self._h2d_stream.wait_event(self._h2d_done[b])     # no-op until the event has been recorded once
                 self._h2d_bufs[b][:nc].copy_(clips[c0:c0 + nc], non_blocking=True)
                 self._h2d_copied[b].record(self._h2d_stream)
             cur.wait_event(self._h2d_copied[b])
