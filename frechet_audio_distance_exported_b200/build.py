@@ -34,7 +34,8 @@ def _nvcc() -> str:
 def _digest() -> str:
     h = hashlib.sha256()
     root = os.path.dirname(HERE)
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(root, "include", "fadb.h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(root, "include", "fadb.h"))
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())
