@@ -458,6 +458,8 @@ int fadb_create(fadb_handle** out, int device) {
     }
     if (const char* e = getenv("FADB_GEMM_SMEM")) h->gemm_smem_budget = atoi(e);
     if (const char* e = getenv("FADB_RESIDENT_B")) h->resident_b = atoi(e);
+    if (const char* e = getenv("FADB_CLUSTER")) h->gemm_cluster = atoi(e);
+    if (const char* e = getenv("FADB_CLUSTER_SIZE")) h->gemm_cluster_size = atoi(e);
     if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
     int rc = gemm_init(h);

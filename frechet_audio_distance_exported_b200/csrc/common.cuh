@@ -98,6 +98,8 @@ struct fadb_handle {
     int fused_front = 1;            // VGGish: PCM -> conv1 output in one kernel (features stay in shared memory)
     int halo = 1;                   // 3x3 layers on large maps: one halo tile per channel block feeds all 9 taps
     int resident_b = 1;             // keep short-K weight slabs resident in smem (see gemm_tc.cu)
+    int gemm_cluster = 1;           // 1 = CTA clusters share weight tiles through TMA multicast (plain single-pass layers)
+    int gemm_cluster_size = 2;      // CTAs per cluster: 2 or 4
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;
     int64_t launches = 0;

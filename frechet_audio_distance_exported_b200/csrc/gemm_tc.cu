@@ -38,10 +38,13 @@ struct GemmParams {
     CUtensorMap tmA[2];   // activations hi, lo : dims (C, W, H, B)
     CUtensorMap tmB[2];   // weights hi, lo     : dims (Ktot, N)
     CUtensorMap tmH;      // halo mode: activations hi with box (64 ch, 10 px, 18 rows, 1 image)
+    CUtensorMap tmBh;     // cluster mode: weights hi with box (64, BN/2): each CTA of a pair loads half and multicasts it
     int W, H, B;
     int BW, BH, BB;       // box; BW*BH*BB == 128
     int tiles_w, tiles_h, tiles_b, tiles_n;
     int num_tiles;
+    int cluster;          // 1, or 2 / 4 = clusters of CTAs walk groups of M tiles of the same N tile and share the weight loads
+    int num_units;        // work units of the static schedule: tiles, or (M-tile group, N tile) in cluster mode
     int cin_blocks;       // Cin / 64
     int taps;             // 9 or 1
     int npass;            // 1 (bf16) or 3 (bf16x3)
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, p.cluster);                 // cluster mode: both CTAs' MMA warps release a stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
@@ -149,8 +152,23 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();       // the peer's barriers exist before anything multicasts to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Static schedule.  Plain mode: unit = tile, N tile fastest.  Cluster mode: unit = (pair of M tiles, N tile); CTA
+    // rank r of the pair takes M tile 2*pair + r, so both CTAs need the SAME weight tile at every K step and each
+    // loads half of it, multicast to both.  An M tile past the end (odd count) runs on zero-filled boxes and stores
+    // nothing (its image index is out of range).
+    const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
+    const int cshift = p.cluster >> 1;               // log2(cluster size) for 1, 2, 4
+    const int unit0 = (int)blockIdx.x >> cshift;
+    const int ustep = (int)gridDim.x >> cshift;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    auto unit_tile = [&](int unit, int& m, int& n0) {
+        const int q = unit / p.tiles_n;
+        n0 = (unit - q * p.tiles_n) * BN;
+        m = (q << cshift) + crank;
+    };
 
     const int kb_per_pass = p.taps * p.cin_blocks;
 
@@ -187,31 +205,49 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         } else {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                int m = tile / p.tiles_n;
-                const int n0 = (tile - m * p.tiles_n) * BN;
+            for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                int m, n0;
+                unit_tile(unit, m, n0);
                 const int wt = m % p.tiles_w; m /= p.tiles_w;
                 const int ht = m % p.tiles_h;
                 const int bt = m / p.tiles_h;
                 const int x0 = wt * p.BW, y0 = ht * p.BH, b0 = bt * p.BB;
+                // K-block walk without integer divisions: this loop paces the whole pipeline (two runtime divisions
+                // per K block in it cost 9 % of the layer time when measured), so (pass, tap, channel block) and the
+                // tap offsets advance incrementally
+                int pass = p.kb_begin / kb_per_pass;
+                int kb = p.kb_begin - pass * kb_per_pass;
+                int tap = kb / p.cin_blocks;
+                int cb = kb - tap * p.cin_blocks;
+                int dy = 0, dx = 0;
+                if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                const uint32_t b_off = kABytes + (p.cluster > 1 ? crank * (Cfg::kBBytes >> cshift) : 0);
+                const int b_row = n0 + (p.cluster > 1 ? crank * (BN >> cshift) : 0);
                 for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg) {
-                    const int pass = kbg / kb_per_pass;
-                    const int kb = kbg - pass * kb_per_pass;
                     const CUtensorMap* ta = &p.tmA[pass == 1 ? 1 : 0];
                     const CUtensorMap* tb = &p.tmB[pass == 2 ? 1 : 0];
-                    const int tap = kb / p.cin_blocks;
-                    const int cb = kb - tap * p.cin_blocks;
-                    int dy = 0, dx = 0;
-                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
                         tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                        tma_load_2d(tb, bar_full + 8 * stage, sa + kABytes, kb * kBlockK, n0);
+                        if (p.cluster > 1)      // my slice of the weight tile, into every CTA of the cluster
+                            tma_load_2d_multicast(&p.tmBh, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row, cmask);
+                        else
+                            tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    ++kb;
+                    if (++cb == p.cin_blocks) {
+                        cb = 0;
+                        ++tap;
+                        if (p.taps == 9 && ++dx == 2) { dx = -1; ++dy; }
+                    }
+                    if (kb == kb_per_pass) {
+                        kb = 0; tap = 0; cb = 0; ++pass;
+                        if (p.taps == 9) { dy = -1; dx = -1; }
+                    }
                 }
             }
         }
@@ -307,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int unit = unit0; unit < p.num_units; unit += ustep, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);    // epilogue drained this accumulator
@@ -325,7 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
                             umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
                         }
-                        umma_commit(bar_empty + 8 * stage);                 // frees the smem stage when MMAs retire
+                        // frees the smem stage when the MMAs retire — in cluster mode on BOTH CTAs: the peer's
+                        // producer multicasts into this stage too and must see it released
+                        if (p.cluster > 1) umma_commit_multicast(bar_empty + 8 * stage, cmask);
+                        else umma_commit(bar_empty + 8 * stage);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -351,11 +390,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         const int hh = t2 % p.BH;
         const int bb = t2 / p.BH;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int unit = unit0; unit < p.num_units; unit += ustep, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            int m = tile / p.tiles_n;
-            const int n0 = (tile - m * p.tiles_n) * BN;
+            int m, n0;
+            unit_tile(unit, m, n0);
             const int wt = m % p.tiles_w; m /= p.tiles_w;
             const int ht = m % p.tiles_h;
             const int bt = m / p.tiles_h;
@@ -499,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();       // no CTA leaves while its peer may still arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -729,6 +769,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     const int bias_bytes = ((L.N * 4 + 127) / 128) * 128;
     const int budget = h->gemm_smem_budget - bias_bytes;
     FADB_REQUIRE(L.N <= 8192, "Cout=%d too large for the shared-memory bias vector", L.N);
+    cudaError_t launch_err = cudaSuccess;
     auto launch = [&](const GemmParams& q) {
         GemmParams pp = q;
         const int b_bytes = BN * kBlockK * 2;
@@ -755,9 +796,51 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             if (pp.stages < 2) pp.stages = 2;
             smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes + bias_bytes;
         }
-        if (BN == 256) fadb_gemm_tc_kernel<256><<<grid, kThreads, smem, st>>>(pp);
-        else if (BN == 128) fadb_gemm_tc_kernel<128><<<grid, kThreads, smem, st>>>(pp);
-        else fadb_gemm_tc_kernel<64><<<grid, kThreads, smem, st>>>(pp);
+        // cluster mode (plain single-pass layers): CTA pairs share every weight tile through TMA multicast, which
+        // halves the L2 -> SM weight traffic of the layers whose operand fetch, not the MMA, limits them
+        pp.cluster = 1;
+        pp.num_units = pp.num_tiles;
+        int g = grid;
+        const int num_m = pp.tiles_w * pp.tiles_h * pp.tiles_b;
+        const int cs = (h->gemm_cluster_size == 4 && BN >= 128) ? 4 : 2;
+        const int pair_units = ((num_m + cs - 1) / cs) * pp.tiles_n;
+        // gemm_cluster = 1: when every CTA pair gets work; 2 (tests): whenever the layer has two M tiles;
+        // 3: only layers with many M tiles per CTA
+        if (h->gemm_cluster && !pp.halo && pp.raw == 0 && npass == 1 && num_m >= 2 &&
+            (h->gemm_cluster == 2 || (h->gemm_cluster == 1 && pair_units >= h->sm_count / cs) ||
+             (h->gemm_cluster == 3 && num_m >= 2 * h->sm_count))) {
+            pp.cluster = cs;
+            pp.num_units = pair_units;
+            g = cs * (h->sm_count / cs);
+            if (encode_weight_map(&pp.tmBh, L.w_hi, L.K, L.N, BN / cs) != FADB_OK) { pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; }
+        }
+        void (*kern)(GemmParams) = (BN == 256) ? fadb_gemm_tc_kernel<256> : (BN == 128 ? fadb_gemm_tc_kernel<128> : fadb_gemm_tc_kernel<64>);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)g);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)pp.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (pp.cluster > 1) {
+            // a persistent kernel wants every cluster co-resident: size the grid to what fits (a GPC with an odd
+            // number of free SMs leaves one without a partner)
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters > 0) {
+                if (nclusters > pp.num_units) nclusters = pp.num_units;
+                cfg.gridDim = dim3((unsigned)(pp.cluster * nclusters));
+            }
+            static const bool verbose = getenv("FADB_VERBOSE") != nullptr;
+            if (verbose)
+                fprintf(stderr, "[fadb] gemm cluster=%d: %d co-resident clusters -> grid %u (units %d, BN %d, smem %d)\n",
+                        pp.cluster, nclusters, cfg.gridDim.x, pp.num_units, BN, smem);
+        }
+        launch_err = cudaLaunchKernelEx(&cfg, kern, pp);
         h->launches++;
     };
     const int nk = npass * io.taps * p.cin_blocks;
@@ -792,6 +875,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                                                  p.out_hi, p.out_lo, p.out_f32);
         h->launches++;
     }
+    FADB_CUDA_CHECK(launch_err);
     if (h->profile) {
         FADB_CUDA_CHECK(cudaEventRecord(ev1, st));
         h->prof_events.push_back(ev0);
