@@ -47,8 +47,10 @@ class Engine:
         self.handle = _lib.Handle(self.device_index)
         self.h = self.handle.ptr
         self.set_precision(precision)
+        self.max_batch = 16384                 # items per network launch (csrc/common.cuh default)
         if max_batch is not None:
             check(self.lib.fadb_set_max_batch(self.h, int(max_batch)))
+            self.max_batch = int(max_batch)
         self.weights_loaded = False
         if state_dict is not None:
             self.load_state_dict(state_dict)

@@ -343,7 +343,7 @@ class FrechetAudioDistance:
             return -1
 
     # ------------------------------------------------------------------ B200 extensions
-    def accumulate_clips(self, clips: torch.Tensor, acc: torch.Tensor, chunk_clips: int = 1024) -> None:
+    def accumulate_clips(self, clips: torch.Tensor, acc: torch.Tensor, chunk_clips: Optional[int] = None) -> None:
         """Embed `clips` ([n, samples] fp32 or raw int16 PCM, HOST or device) and add their rows to the fp64 statistics
         buffer `acc`.  Host tensors are streamed in chunks through two device buffers on a copy
         stream so the host->device copy of chunk i+1 overlaps the kernels of chunk i (pin the host
@@ -356,6 +356,11 @@ class FrechetAudioDistance:
             eng.stats_accumulate(eng.embed_pcm(clips if clips.dtype == torch.int16 else clips.to(torch.float32)), acc)
             return
         assert clips.dtype in (torch.float32, torch.int16) and clips.dim() == 2 and clips.is_contiguous()
+        if chunk_clips is None:
+            # one chunk = one full batch of the network (VGGish: max_batch patches), so the streamed path launches the
+            # same large kernels as a device-resident call; other models batch internally
+            rows = eng.frontend_rows(clips.shape[1]) if self.model_name == "vggish" else 0
+            chunk_clips = max(1, eng.max_batch // rows) if rows > 0 else 1024
         chunk = min(chunk_clips, n)
         cur = torch.cuda.current_stream()
         if (getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1])
