@@ -388,85 +388,8 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused VGGish kernel: one CTA = one 96-frame patch.  Phase 1 (fp64 FFT, shared-memory bound): 8 warps x 12
-// frames write the log-mel patch into a shared-memory tile.  Phase 2 (packed fp32 FMAs): conv3x3(1->64) +
-// bias + ReLU + maxpool2x2 straight from that tile to NHWC bf16.  The fp32 features never touch HBM, and
-// with two CTAs per SM the FFT phase of one patch overlaps the FMA phase of another (different pipes).
-// ------------------------------------------------------------------------------------------------
-struct FusedSmem {
-    using S = FrontSmem<512>;
-    static constexpr int kTilePitch = 68;                                     // 64 mel + halo, 16-byte rows
-    static constexpr int kTileBytes = 98 * kTilePitch * 4;                    // 96 frames + 2 halo rows
-    static constexpr int kWBytes = 9 * 64 * 4 + 64 * 4;
-    static constexpr int kTotal = S::kTotal + kTileBytes + kWBytes;
-};
-
-__global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_kernel(
-    const FrontParams p, const float* __restrict__ conv_w, const float* __restrict__ conv_b, int patches_per_clip,
-    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-    constexpr int NF = 512, M = 256;
-    using S = FrontSmem<NF>;
-    extern __shared__ __align__(16) uint8_t fsm[];
-    double2* s_tw = reinterpret_cast<double2*>(fsm);
-    double* s_win = reinterpret_cast<double*>(fsm + S::kTwBytes);
-    double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);
-    double2* s_buf = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes);
-    float* s_spec = reinterpret_cast<float*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes + S::kBufBytes);
-    float* s_wt = s_spec + S::kSpecBytes / 4;
-    float (*s_tile)[FusedSmem::kTilePitch] = reinterpret_cast<float (*)[FusedSmem::kTilePitch]>(fsm + S::kTotal);
-    float (*s_w)[64] = reinterpret_cast<float (*)[64]>(fsm + S::kTotal + FusedSmem::kTileBytes);
-    float* s_b = reinterpret_cast<float*>(fsm + S::kTotal + FusedSmem::kTileBytes + 9 * 64 * 4);
-
-    for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
-    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
-    build_pass_twiddles<M, NF>(s_ptw, p.tw);
-    for (int i = threadIdx.x; i < p.wt_rows * 32; i += kFrontWarps * 32) s_wt[i] = p.band_wt[i];
-    for (int i = threadIdx.x; i < 9 * 64; i += kFrontWarps * 32) s_w[i / 64][i % 64] = conv_w[i];
-    if (threadIdx.x < 64) s_b[threadIdx.x] = conv_b[threadIdx.x];
-    // zero halo: rows 0 and 97, columns 0 and 65 (tile row r holds frame r-1, column c holds mel c-1)
-    for (int i = threadIdx.x; i < 2 * FusedSmem::kTilePitch; i += kFrontWarps * 32)
-        s_tile[(i / FusedSmem::kTilePitch) * 97][i % FusedSmem::kTilePitch] = 0.f;
-    for (int i = threadIdx.x; i < 98; i += kFrontWarps * 32) { s_tile[i][0] = 0.f; s_tile[i][65] = 0.f; }
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2* x = s_buf + warp * S::kBufSlots;
-    float* spec = s_spec + warp * S::kSpecPitch;
-    const int clip = blockIdx.y, patch = blockIdx.x;
-    const PcmView pcm = clip_view(p.pcm, p.pcm_i16, clip, p.pcm_stride);
-    int bst[2], bln[2];
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-        bst[h2] = p.band_start[lane + 32 * h2];
-        bln[h2] = p.band_len[lane + 32 * h2];
-    }
-    // ---- phase 1: 96 frames of this patch -> s_tile rows 1..96, columns 1..64
-    for (int fi = 0; fi < 12; ++fi) {
-        const int fr = warp * 12 + fi;
-        frame_logmel<NF>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, s_wt, bst, bln, &s_tile[fr + 1][1]);
-    }
-    __syncthreads();
-    // ---- phase 2: conv1 + ReLU + maxpool; thread = pooled pixel (warp = pooled row within a band of 8)
-    const size_t pbase = (size_t)clip * patches_per_clip + patch;
-#pragma unroll 1
-    for (int band = 0; band < 6; ++band) {
-        const int prow = band * 8 + warp;              // pooled row 0..47
-        unsigned long long in[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            // input rows 2*prow-1 .. 2*prow+2  -> tile rows 2*prow .. 2*prow+3 ; input cols 2*lane-1.. -> tile cols 2*lane..
-            const float2 a = *reinterpret_cast<const float2*>(&s_tile[2 * prow + r][2 * lane]);
-            const float2 b = *reinterpret_cast<const float2*>(&s_tile[2 * prow + r][2 * lane + 2]);
-            in[r][0] = pack_f32x2(a.x, a.x); in[r][1] = pack_f32x2(a.y, a.y);
-            in[r][2] = pack_f32x2(b.x, b.x); in[r][3] = pack_f32x2(b.y, b.y);
-        }
-        const size_t obase = ((pbase * 48 + prow) * 32 + lane) * 64;
-        conv1_vggish_pixel(in, s_w, s_b, out_hi, out_lo, obase);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused VGGish kernel, tensor-core conv1.  Same phase 1; phase 2 runs conv3x3(1->64) as a tcgen05 GEMM:
+// Fused VGGish kernel.  Phase 1 (fp64 FFT, shared-memory / latency bound): 8 warps x 12 frames write the log-mel
+// patch into a shared-memory tile, so the fp32 features never touch HBM.  Phase 2 runs conv3x3(1->64) as a tcgen05 GEMM:
 //   D[pixel, cout] = sum_k A[pixel, k] * B[cout, k],  K = 32 = 27 used columns:
 //     A = [x_hi(tap 0..7) | x_lo(tap 0..7) | x_hi(tap 0..7) | x_hi8, x_lo8, x_hi8, 0...]
 //     B = [w_hi(tap 0..7) | w_hi(tap 0..7) | w_lo(tap 0..7) | w_hi8, w_hi8, w_lo8, 0...]
@@ -494,8 +417,7 @@ struct FusedTcSmem {
 
 __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_tc_kernel(
     const FrontParams p, const float* __restrict__ conv_w, const float* __restrict__ conv_b, int patches_per_clip,
-    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, uint32_t desc_lbo,
-    uint32_t desc_sbo, int* err_flag, int dbg) {
+    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int* err_flag, int dbg) {
     constexpr int NF = 512, M = 256;
     using S = FrontSmem<NF>;
     using F = FusedTcSmem;
@@ -549,7 +471,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
     const uint32_t a_row_off = (uint32_t)(bw >> 3) * sbo + (uint32_t)(bw & 7) * 16;
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t a_base = smem_u32(s_bufb);
-    const uint64_t db = make_nosw_desc(smem_u32(s_b), desc_lbo, desc_sbo);
+    const uint64_t db = make_nosw_desc(smem_u32(s_b), lbo, sbo);
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
 
 #pragma unroll 1
@@ -606,7 +528,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                     tc_fence_after();
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint64_t da = make_nosw_desc(a_base + q * F::kATileBytes, desc_lbo, desc_sbo);
+                        const uint64_t da = make_nosw_desc(a_base + q * F::kATileBytes, lbo, sbo);
                         umma_bf16(tmem_base + q * 64, da, db, idesc, 0u);
                         umma_bf16(tmem_base + q * 64, da + ((2 * lbo) >> 4), db + ((2 * lbo) >> 4), idesc, 1u);   // K 16..31
                     }
@@ -783,8 +705,6 @@ int frontend_init(fadb_handle* h) {
                                          front_smem<1024>()));
     FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_vggish_front_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          FusedTcSmem::kTotal));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_vggish_front_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         FusedSmem::kTotal));
     return FADB_OK;
 }
 
@@ -850,21 +770,12 @@ int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64
     p.frames_valid = p.rows_out;
     dim3 grid((unsigned)patches, (unsigned)n_clips);
     FrontProfile prof(h, st);
-    static const bool tc_conv1 = !(getenv("FADB_TC_CONV1") && atoi(getenv("FADB_TC_CONV1")) == 0);
-    static const int front_dbg = getenv("FADB_FRONT_DBG") ? atoi(getenv("FADB_FRONT_DBG")) : 0;            // bring-up only
-    static const bool desc_swap = getenv("FADB_C1_DESC_SWAP") && atoi(getenv("FADB_C1_DESC_SWAP")) != 0;   // bring-up only
+    static const int front_dbg = getenv("FADB_FRONT_DBG") ? atoi(getenv("FADB_FRONT_DBG")) : 0;   // profiling only: 1 / 2 skip a phase
     __nv_bfloat16* lo = h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr;
-    if (tc_conv1) {
-        const int64_t total = patches * n_clips;
-        const int64_t slots = 2LL * h->sm_count;
-        fadb_vggish_front_conv1_tc_kernel<<<(unsigned)(total < slots ? total : slots), kFrontWarps * 32, FusedTcSmem::kTotal, st>>>(
-            p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo,
-            desc_swap ? FusedTcSmem::kSbo : FusedTcSmem::kLbo, desc_swap ? FusedTcSmem::kLbo : FusedTcSmem::kSbo, h->err_flag,
-            front_dbg);
-    }
-    else
-        fadb_vggish_front_conv1_kernel<<<grid, kFrontWarps * 32, FusedSmem::kTotal, st>>>(
-            p, h->conv1_w, h->conv1_b, (int)patches, out_hi, lo);
+    const int64_t total = patches * n_clips;
+    const int64_t slots = 2LL * h->sm_count;
+    fadb_vggish_front_conv1_tc_kernel<<<(unsigned)(total < slots ? total : slots), kFrontWarps * 32, FusedTcSmem::kTotal, st>>>(
+        p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo, h->err_flag, front_dbg);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;

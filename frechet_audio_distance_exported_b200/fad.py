@@ -357,10 +357,7 @@ class FrechetAudioDistance:
             return
         assert clips.dtype in (torch.float32, torch.int16) and clips.dim() == 2 and clips.is_contiguous()
         if chunk_clips is None:
-            # one chunk = one full batch of the network (VGGish: max_batch patches), so the streamed path launches the
-            # same large kernels as a device-resident call; other models batch internally
-            rows = eng.frontend_rows(clips.shape[1]) if self.model_name == "vggish" else 0
-            chunk_clips = max(1, eng.max_batch // rows) if rows > 0 else 1024
+            chunk_clips = 512          # measured on B200 (tools/prof_e2e.py): 256 .. 1024 are within 2 %, 384 - 512 best
         chunk = min(chunk_clips, n)
         cur = torch.cuda.current_stream()
         if (getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1])
@@ -374,9 +371,9 @@ class FrechetAudioDistance:
             self._h2d_stream.wait_stream(cur)                  # fresh buffers: order after whatever ran before
         # The copy stream only ever waits for the kernels that last READ the buffer it is about to overwrite
         # (events persist across calls), so the first copy of a set overlaps the tail of the previous set; the
-        # first chunk of a call is small, so the kernels start after a quarter of a chunk's copy time.
+        # first chunk of a call is half size, so the kernels start after half a chunk's copy time.
         bounds, c0 = [], 0
-        first = max(1, chunk // 4) if n > chunk else chunk
+        first = max(1, chunk // 2) if n > chunk else chunk
         while c0 < n:
             nc = min(first if c0 == 0 else chunk, n - c0)
             bounds.append((c0, nc))

@@ -21,5 +21,5 @@ torch.cuda.synchronize()
 ms, fl, nl = eng.profile_read()
 fm = eng.front_ms / 3
 gb = n * (640000 + 10 * 48 * 32 * 64 * 2) / 1e9
-print(f"TC_CONV1={os.environ.get('FADB_TC_CONV1', '1')} DBG={os.environ.get('FADB_FRONT_DBG', '0')}: front+conv1 {fm:.3f} ms / {n} clips "
+print(f"DBG={os.environ.get('FADB_FRONT_DBG', '0')}: front+conv1 {fm:.3f} ms / {n} clips "
       f"({n / fm * 1e3:.0f} clips/s, {gb / fm * 1e3:.0f} GB/s of PCM-in + bf16-out); tensor layers {ms / 3:.3f} ms ({fl / ms / 1e9:.0f} TFLOP/s)")
