@@ -15,6 +15,8 @@ sum x x^T} -> (one NCCL all-reduce) -> mean/cov -> Frechet distance.
           chunked H2D copies and the D2H read of the FAD scalar are inside the timed region
   roofline     : the tcgen05 implicit-GEMM kernel (all 8 tensor-core layers): algorithmic FLOPs / summed
                  per-launch CUDA-event durations, against the measured sustained bf16 peak
+  frontend     : the fused front-end (+ conv1) kernel: SURVEY 8d bytes per clip / its launch time, against the HBM peak
+  e2e_pcm16    : like e2e, from pinned raw int16 PCM (the reference's dtype="int16" path; half the host -> device bytes)
   cpu_baseline : the oracle port of the reference's per-clip CPU path on a bounded sample (rank 0, N = 1)
 """
 from __future__ import annotations

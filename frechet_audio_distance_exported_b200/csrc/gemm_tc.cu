@@ -831,9 +831,17 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             // a persistent kernel wants every cluster co-resident: size the grid to what fits (a GPC with an odd
             // number of free SMs leaves one without a partner)
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters > 0) {
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess &&
+                nclusters * pp.cluster * 10 >= h->sm_count * 9) {
                 if (nclusters > pp.num_units) nclusters = pp.num_units;
                 cfg.gridDim = dim3((unsigned)(pp.cluster * nclusters));
+            } else {
+                // no answer, or clusters would leave more than a tenth of the SMs idle: plain launch
+                (void)cudaGetLastError();
+                pp.cluster = 1;
+                pp.num_units = pp.num_tiles;
+                attr[0].val.clusterDim.x = 1;
+                cfg.gridDim = dim3((unsigned)grid);
             }
             static const bool verbose = getenv("FADB_VERBOSE") != nullptr;
             if (verbose)
