@@ -3,7 +3,7 @@
 // Replaces calculate_embd_statistics (fad.py:483-496: mu = np.mean, sigma = np.cov(rowvar=False), ddof = 1)
 // — SURVEY.md §2.2 K10.  acc = { n, sum (x-K), sum (x-K)(x-K)^T } in fp64 (K = optional common shift),
 // so partials from batches / GPUs add (NCCL allreduce between accumulate and finalize).
-// The d x d second moment is an fp64 DFMA syrk over 64x64 upper-triangular tiles, rows split across
+// The d x d second moment is an fp64 DFMA syrk over 128x128 upper-triangular tiles, rows split across
 // CTAs, one fp64 atomicAdd flush per CTA tile.
 #include "common.cuh"
 
@@ -28,13 +28,19 @@ __global__ void __launch_bounds__(256) stats_colsum_kernel(const TIn* __restrict
 }
 
 // ---------------------------------------------------------------- syrk: S += (X-K)^T (X-K), upper tiles
-constexpr int TS = 64;   // output tile
-constexpr int KC = 32;   // rows per smem chunk
+// fp64 DFMA, 128 x 128 output tile per CTA, 8 x 8 register tile per thread (256 threads = 16 x 16).  A thread owns
+// rows {2ty, 2ty+1} + 32q and columns {2tx, 2tx+1} + 32q of the tile, so every operand load is one 16-byte word
+// that is contiguous across the 16 lanes of a half warp: conflict-free, 8 LDS.128 per 64 DFMA.  (The first version
+// used 64 x 64 tiles with 4 contiguous outputs per thread: its operand loads were 4-way bank conflicted and it
+// reached a quarter of the fp64 rate.)  Rows are staged 16 at a time as (x - K) in fp64; the next chunk's global
+// loads are in flight while the current one is multiplied.
+constexpr int TS = 128;  // output tile
+constexpr int KC = 16;   // rows per smem chunk
 
 template <typename TIn>
-__global__ void __launch_bounds__(256) stats_syrk_kernel(const TIn* __restrict__ x, long long n, int d, long long ld,
-                                                         const double* __restrict__ shift, double* __restrict__ S,
-                                                         int ntile, long long rows_per_cta) {
+__global__ void __launch_bounds__(256, 1) stats_syrk_kernel(const TIn* __restrict__ x, long long n, int d, long long ld,
+                                                            const double* __restrict__ shift, double* __restrict__ S,
+                                                            int ntile, long long rows_per_cta) {
     // decode upper-triangular tile pair
     int pair = blockIdx.x, ti = 0;
     while (pair >= ntile - ti) { pair -= ntile - ti; ++ti; }
@@ -46,48 +52,60 @@ __global__ void __launch_bounds__(256) stats_syrk_kernel(const TIn* __restrict__
 
     __shared__ __align__(16) double sa[KC][TS];
     __shared__ __align__(16) double sb[KC][TS];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4 x 4 outputs each
-    double acc[4][4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
     const int ci0 = ti * TS, cj0 = tj * TS;
+    // staging role: element e = tid + 256 i of the KC x TS chunk -> row e / TS, column e % TS (coalesced rows)
+    const int sc = threadIdx.x & (TS - 1);
+    const int sr0 = threadIdx.x / TS;                       // 0 or 1; rows sr0 + 2 i
+    const double ka = (shift && ci0 + sc < d) ? shift[ci0 + sc] : 0.0;
+    const double kb = (shift && cj0 + sc < d) ? shift[cj0 + sc] : 0.0;
+    const bool ina = ci0 + sc < d, inb = cj0 + sc < d;
+    double pa[KC / 2], pb[KC / 2];
+    auto fetch = [&](long long rb) {
+#pragma unroll
+        for (int i = 0; i < KC / 2; ++i) {
+            const long long r = rb + sr0 + 2 * i;
+            pa[i] = (r < r1 && ina) ? (double)__ldg(x + r * ld + ci0 + sc) - ka : 0.0;
+            pb[i] = (r < r1 && inb) ? (double)__ldg(x + r * ld + cj0 + sc) - kb : 0.0;
+        }
+    };
+    fetch(r0);
     for (long long rb = r0; rb < r1; rb += KC) {
-        // stage KC rows of both column tiles as (x - K) in fp64; out-of-range -> 0
-        for (int e = threadIdx.x; e < KC * TS; e += 256) {
-            const int rr = e / TS, cc = e % TS;
-            const long long r = rb + rr;
-            double va = 0.0, vb = 0.0;
-            if (r < r1) {
-                if (ci0 + cc < d) va = (double)__ldg(x + r * ld + ci0 + cc) - (shift ? shift[ci0 + cc] : 0.0);
-                if (cj0 + cc < d) vb = (double)__ldg(x + r * ld + cj0 + cc) - (shift ? shift[cj0 + cc] : 0.0);
-            }
-            sa[rr][cc] = va;
-            sb[rr][cc] = vb;
+#pragma unroll
+        for (int i = 0; i < KC / 2; ++i) {
+            sa[sr0 + 2 * i][sc] = pa[i];
+            sb[sr0 + 2 * i][sc] = pb[i];
         }
         __syncthreads();
-#pragma unroll 8
+        if (rb + KC < r1) fetch(rb + KC);                   // next chunk's loads overlap this chunk's FMAs
+#pragma unroll 4
         for (int k = 0; k < KC; ++k) {
-            const double2 a01 = *reinterpret_cast<const double2*>(&sa[k][ty * 4]);
-            const double2 a23 = *reinterpret_cast<const double2*>(&sa[k][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2*>(&sb[k][tx * 4]);
-            const double2 b23 = *reinterpret_cast<const double2*>(&sb[k][tx * 4 + 2]);
-            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-            const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+            double a[8], b[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int q = 0; q < 4; ++q) {
+                const double2 av = *reinterpret_cast<const double2*>(&sa[k][2 * ty + 32 * q]);
+                const double2 bv = *reinterpret_cast<const double2*>(&sb[k][2 * tx + 32 * q]);
+                a[2 * q] = av.x; a[2 * q + 1] = av.y;
+                b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gi = ci0 + ty * 4 + i, gj = cj0 + tx * 4 + j;
+        for (int j = 0; j < 8; ++j) {
+            const int gi = ci0 + 2 * ty + 32 * (i >> 1) + (i & 1), gj = cj0 + 2 * tx + 32 * (j >> 1) + (j & 1);
             if (gi < d && gj < d) atomicAdd(S + (size_t)gi * d + gj, acc[i][j]);
         }
 }
@@ -125,7 +143,7 @@ static int stats_accumulate_t(fadb_handle* h, const TIn* emb, int64_t n, int d, 
     {
         const int ntile = (d + TS - 1) / TS;
         const int npair = ntile * (ntile + 1) / 2;
-        long long want = (4LL * h->sm_count + npair - 1) / npair;           // row splits to fill the machine
+        long long want = (2LL * h->sm_count + npair - 1) / npair;           // row splits to fill the machine
         long long rows_per = (n + want - 1) / want;
         if (rows_per < 256) rows_per = 256;
         rows_per = (rows_per + KC - 1) / KC * KC;
