@@ -44,6 +44,8 @@ struct GemmParams {
     int tiles_w, tiles_h, tiles_b, tiles_n;
     int num_tiles;
     int cluster;          // 1, or 2 / 4 = clusters of CTAs walk groups of M tiles of the same N tile and share the weight loads
+    int twocta;           // cluster == 2 only: 1 = ONE tcgen05.mma.cta_group::2 (M = 256) per K step for the CTA pair, issued by
+                          // rank 0; each CTA keeps A (its 128 rows) and half of the weight tile, nothing is duplicated
     int num_units;        // work units of the static schedule: tiles, or (M-tile group, N tile) in cluster mode
     int cin_blocks;       // Cin / 64
     int taps;             // 9 or 1
@@ -92,7 +94,9 @@ struct GemmCfg {
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// PAIR = the cta_group::2 variant (clusters of two only).  It is a separate instantiation because a kernel that contains
+// cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     const int kStages = p.stages;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     // layout: [resident B: nkb x kBBytes (resb only)] [stages] ([halo mode: B ring]) [barriers]
     const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * Cfg::kBBytes : 0;
-    const int stage_pitch = p.halo ? kHaloBytes : Cfg::kStageBytes;
+    const int stage_pitch = p.halo ? kHaloBytes : (PAIR ? kABytes + Cfg::kBBytes / 2 : Cfg::kStageBytes);
     const uint32_t stage_base = base + res_bytes;
     const uint32_t bring_base = stage_base + kStages * stage_pitch;           // halo mode only
     const int bring_bytes = (p.halo && !p.resb) ? p.b_stages * Cfg::kBBytes : 0;
@@ -136,11 +140,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, p.cluster);                 // cluster mode: both CTAs' MMA warps release a stage
+            mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster);  // multicast mode: both CTAs' MMA warps release a stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 8);                        // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * s, PAIR ? 16 : 8);        // one arrive per epilogue warp (of both CTAs in pair mode)
         }
         mbar_init(bar_bres, 1);
         for (int s = 0; s < 8; ++s) {
@@ -149,7 +153,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    if (warp == 2) {
+        if constexpr (PAIR) tmem_alloc_2sm(smem_u32(tmem_slot), Cfg::kTmemCols);
+        else tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();       // the peer's barriers exist before anything multicasts to them
@@ -228,13 +235,23 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     const CUtensorMap* tb = &p.tmB[pass == 2 ? 1 : 0];
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
-                    if (elect_one()) {
+                    if constexpr (PAIR) {
+                        // pair mode: both CTAs' loads complete on the LEADER's barrier, which expects all of them
+                        if (elect_one()) {
+                            const uint32_t lead_full = mapa_rank(bar_full + 8 * stage, 0);
+                            if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)stage_pitch);
+                            tma_load_4d_2sm(ta, lead_full, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                            tma_load_2d_2sm(&p.tmBh, lead_full, sa + kABytes, kb * kBlockK, n0 + crank * (BN / 2));
+                        }
+                    } else {
+                      if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
                         tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
                         if (p.cluster > 1)      // my slice of the weight tile, into every CTA of the cluster
                             tma_load_2d_multicast(&p.tmBh, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row, cmask);
                         else
                             tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row);
+                      }
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -334,6 +351,39 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             if (elect_one()) umma_commit(bar_tfull + 8 * as);
             __syncwarp();
         }
+    } else if (warp == 1 && PAIR) {
+        // ======================= MMA issuer, pair mode: rank 0 issues M = 256 MMAs for both CTAs =======
+        if constexpr (PAIR) if (crank == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                                       (uint32_t((2 * kTileM) >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = unit0; unit < p.num_units; unit += ustep, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);    // both CTAs' epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // both CTAs' TMA bytes landed
+                    tc_fence_after();
+                    const uint32_t sa = stage_base + stage * stage_pitch;
+                    const uint64_t da = make_sw128_desc(sa);
+                    const uint64_t db = make_sw128_desc(sa + kABytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
+                        umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)0x3);   // stage free again, in both CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                if (elect_one()) umma_commit_2sm(bar_tfull + 8 * as, (uint16_t)0x3);   // both epilogues may drain
+                __syncwarp();
+            }
+        }
     } else if (warp == 1) {
         // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) =======
         {
@@ -423,7 +473,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+                    if (lane == 0) {
+                        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * as, 0));   // the leader's MMA warp waits
+                        else mbar_arrive(bar_tempty + 8 * as);
+                    }
                 }
                 float v[32];
                 if (p.raw) {
@@ -541,7 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     if (p.cluster > 1) cluster_sync_all();       // no CTA leaves while its peer may still arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -630,11 +684,17 @@ int gemm_init(fadb_handle* h) {
         }
         g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmCfg<64>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmCfg<128>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<256>::kMaxSmemBytes));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<64>::kMaxSmemBytes));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<128>::kMaxSmemBytes));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmCfg<256>::kMaxSmemBytes));
     return FADB_OK;
 }
@@ -796,6 +856,13 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             if (pp.stages < 2) pp.stages = 2;
             smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes + bias_bytes;
         }
+        const int smem_plain = smem, stages_plain = pp.stages;
+        int smem_pair = smem, stages_pair = pp.stages;       // pair mode keeps only half of the weight tile per CTA
+        if (!pp.halo) {
+            stages_pair = budget / (kABytes + b_bytes / 2);
+            if (stages_pair > 8) stages_pair = 8;
+            smem_pair = stages_pair * (kABytes + b_bytes / 2) + GemmCfg<64>::kExtraBytes + bias_bytes;
+        }
         // cluster mode (plain single-pass layers): CTA pairs share every weight tile through TMA multicast, which
         // halves the L2 -> SM weight traffic of the layers whose operand fetch, not the MMA, limits them
         pp.cluster = 1;
@@ -811,10 +878,16 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
              (h->gemm_cluster == 3 && num_m >= 2 * h->sm_count))) {
             pp.cluster = cs;
             pp.num_units = pair_units;
+            if (h->gemm_twocta && cs == 2) { pp.twocta = 1; pp.stages = stages_pair; smem = smem_pair; }
             g = cs * (h->sm_count / cs);
             if (encode_weight_map(&pp.tmBh, L.w_hi, L.K, L.N, BN / cs) != FADB_OK) { pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; }
         }
-        void (*kern)(GemmParams) = (BN == 256) ? fadb_gemm_tc_kernel<256> : (BN == 128 ? fadb_gemm_tc_kernel<128> : fadb_gemm_tc_kernel<64>);
+        void (*kern)(GemmParams) = (BN == 256) ? fadb_gemm_tc_kernel<256, false>
+                                   : (BN == 128 ? fadb_gemm_tc_kernel<128, false> : fadb_gemm_tc_kernel<64, false>);
+        void (*kern_pair)(GemmParams) = (BN == 256) ? fadb_gemm_tc_kernel<256, true>
+                                        : (BN == 128 ? fadb_gemm_tc_kernel<128, true> : fadb_gemm_tc_kernel<64, true>);
+        void (*kern_plain)(GemmParams) = kern;
+        if (pp.twocta) kern = kern_pair;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)g);
         cfg.blockDim = dim3(kThreads);
@@ -839,6 +912,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                 // no answer, or clusters would leave more than a tenth of the SMs idle: plain launch
                 (void)cudaGetLastError();
                 pp.cluster = 1;
+                if (pp.twocta) { pp.twocta = 0; pp.stages = stages_plain; cfg.dynamicSmemBytes = (size_t)smem_plain; kern = kern_plain; }
                 pp.num_units = pp.num_tiles;
                 attr[0].val.clusterDim.x = 1;
                 cfg.gridDim = dim3((unsigned)grid);
