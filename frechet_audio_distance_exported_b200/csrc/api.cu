@@ -461,6 +461,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_CLUSTER")) h->gemm_cluster = atoi(e);
     if (const char* e = getenv("FADB_CLUSTER_SIZE")) h->gemm_cluster_size = atoi(e);
     if (const char* e = getenv("FADB_TWOCTA")) h->gemm_twocta = atoi(e);
+    if (const char* e = getenv("FADB_PAIR_HALO")) h->gemm_pair_halo = atoi(e);
     if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
     int rc = gemm_init(h);

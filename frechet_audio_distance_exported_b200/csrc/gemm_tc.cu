@@ -106,11 +106,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     uint8_t* smem = smem_raw + (base - raw_addr);
 
     // layout: [resident B: nkb x kBBytes (resb only)] [stages] ([halo mode: B ring]) [barriers]
-    const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * Cfg::kBBytes : 0;
+    constexpr int kBTile = PAIR ? Cfg::kBBytes / 2 : Cfg::kBBytes;   // bytes of one weight K block held by THIS CTA
+    const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * kBTile : 0;
     const int stage_pitch = p.halo ? kHaloBytes : (PAIR ? kABytes + Cfg::kBBytes / 2 : Cfg::kStageBytes);
     const uint32_t stage_base = base + res_bytes;
     const uint32_t bring_base = stage_base + kStages * stage_pitch;           // halo mode only
-    const int bring_bytes = (p.halo && !p.resb) ? p.b_stages * Cfg::kBBytes : 0;
+    const int bring_bytes = (p.halo && !p.resb) ? p.b_stages * kBTile : 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + res_bytes + kStages * stage_pitch + bring_bytes);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages]
@@ -179,31 +180,55 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     const int kb_per_pass = p.taps * p.cin_blocks;
 
+    // pair mode (halo path): every load completes on the LEADER's barrier, which expects the bytes of both CTAs; each CTA
+    // loads its own activations and its half of the weight rows; the leader alone issues and commits for both
+    auto expect = [&](uint32_t bar, uint32_t bytes_per_cta) {
+        if constexpr (PAIR) { if (crank == 0) mbar_arrive_expect_tx(bar, 2u * bytes_per_cta); }
+        else mbar_arrive_expect_tx(bar, bytes_per_cta);
+    };
+    auto load_act = [&](const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+        if constexpr (PAIR) tma_load_4d_2sm(m, mapa_rank(bar, 0), dst, c0, c1, c2, c3);
+        else tma_load_4d(m, bar, dst, c0, c1, c2, c3);
+    };
+    auto load_wgt = [&](uint32_t bar, uint32_t dst, int k0, int n0) {
+        if constexpr (PAIR) tma_load_2d_2sm(&p.tmBh, mapa_rank(bar, 0), dst, k0, n0 + crank * (BN / 2));
+        else tma_load_2d(&p.tmB[0], bar, dst, k0, n0);
+    };
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+        if constexpr (PAIR) umma_bf16_2sm(d, da, db, idesc, acc);
+        else umma_bf16(d, da, db, idesc, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+        if constexpr (PAIR) umma_commit_2sm(bar, (uint16_t)0x3);
+        else umma_commit(bar);
+    };
+
     if (warp == 0) {
         // ======================= TMA producer (whole warp runs the loop; one elected lane issues) =====
         if (p.halo) {
             // halo mode: ONE activation load per (tile, channel block) serves all 9 taps
             int stage = 0;
             uint32_t phase = 0;
-            if (p.resb && blockIdx.x < p.num_tiles) {
+            if (p.resb && unit0 < p.num_units) {
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(bar_bres, (uint32_t)res_bytes);
+                    expect(bar_bres, (uint32_t)res_bytes);
                     for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
-                        tma_load_2d(&p.tmB[0], bar_bres, base + (kbg - p.kb_begin) * Cfg::kBBytes, kbg * kBlockK, 0);
+                        load_wgt(bar_bres, base + (kbg - p.kb_begin) * kBTile, kbg * kBlockK, 0);
                 }
                 __syncwarp();
             }
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                int m = tile / p.tiles_n;
+            for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                int m, n0;
+                unit_tile(unit, m, n0);
                 const int wt = m % p.tiles_w; m /= p.tiles_w;
                 const int ht = m % p.tiles_h;
                 const int bt = m / p.tiles_h;
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)kHaloBoxBytes);
-                        tma_load_4d(&p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes, cb * kBlockK,
-                                    wt * p.BW - 1, ht * p.BH - 1, bt);
+                        expect(bar_full + 8 * stage, (uint32_t)kHaloBoxBytes);
+                        load_act(&p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes, cb * kBlockK,
+                                 wt * p.BW - 1, ht * p.BH - 1, bt);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -273,15 +298,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         if (p.halo && !p.resb) {
             int bs = 0;
             uint32_t bphase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int n0 = (tile % p.tiles_n) * BN;
+            for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                int m, n0;
+                unit_tile(unit, m, n0);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(bar_bfull + 8 * bs, (uint32_t)Cfg::kBBytes);
-                            tma_load_2d(&p.tmB[0], bar_bfull + 8 * bs, bring_base + bs * Cfg::kBBytes,
-                                        (tap * p.cin_blocks + cb) * kBlockK, n0);
+                            expect(bar_bfull + 8 * bs, (uint32_t)kBTile);
+                            load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (tap * p.cin_blocks + cb) * kBlockK, n0);
                         }
                         __syncwarp();
                         if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
@@ -292,14 +317,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     } else if (warp == 1 && p.halo) {
         // ======================= MMA issuer, halo mode =======================
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
-                                   (uint32_t(kTileM >> 4) << 24);
+                                   (uint32_t((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
         int stage = 0, bs = 0, it = 0;
         uint32_t phase = 0, bphase = 0;
-        if (p.resb && blockIdx.x < p.num_tiles) {
+        const bool issuer = !PAIR || crank == 0;                // pair mode: the leader issues for both CTAs
+        if (issuer && p.resb && unit0 < p.num_units) {
             mbar_wait(bar_bres, 0, p.err_flag);
             tc_fence_after();
         }
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int unit = unit0; issuer && unit < p.num_units; unit += ustep, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);
@@ -314,8 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 tc_fence_after();
                 const uint64_t da0 = make_halo_desc(stage_base + stage * kHaloBytes);
                 if (p.resb) {
-                    const uint64_t db0 = make_sw128_desc(base + cb * Cfg::kBBytes);
-                    const uint32_t bstep = (uint32_t)(p.cin_blocks * Cfg::kBBytes) >> 4;   // next tap, same channel block
+                    const uint64_t db0 = make_sw128_desc(base + cb * kBTile);
+                    const uint32_t bstep = (uint32_t)(p.cin_blocks * kBTile) >> 4;   // next tap, same channel block
                     if (elect_one()) {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
@@ -323,9 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             const uint64_t db = db0 + (uint64_t)(tap * bstep);
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k)
-                                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                                mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
                         }
-                        umma_commit(bar_empty + 8 * stage);                 // halo tile free again
+                        commit(bar_empty + 8 * stage);                 // halo tile free again
                     }
                     __syncwarp();
                 } else {
@@ -334,13 +360,13 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
                         tc_fence_after();
                         const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);
-                        const uint64_t db = make_sw128_desc(bring_base + bs * Cfg::kBBytes);
+                        const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k)
-                                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
-                            umma_commit(bar_bempty + 8 * bs);
-                            if (tap == 8) umma_commit(bar_empty + 8 * stage);
+                                mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                            commit(bar_bempty + 8 * bs);
+                            if (tap == 8) commit(bar_empty + 8 * stage);
                         }
                         __syncwarp();
                         if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
@@ -348,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            if (elect_one()) umma_commit(bar_tfull + 8 * as);
+            if (elect_one()) commit(bar_tfull + 8 * as);
             __syncwarp();
         }
     } else if (warp == 1 && PAIR) {
@@ -832,37 +858,41 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     cudaError_t launch_err = cudaSuccess;
     auto launch = [&](const GemmParams& q) {
         GemmParams pp = q;
-        const int b_bytes = BN * kBlockK * 2;
-        const int res = (pp.kb_end - pp.kb_begin) * b_bytes;
-        int smem;
-        if (pp.halo && pp.raw == 0) {
-            pp.resb = (h->resident_b && pp.tiles_n == 1 && res + 2 * kHaloBytes <= budget) ? 1 : 0;
-            if (pp.resb) {
-                pp.b_stages = 0;
-                pp.stages = (budget - res) / kHaloBytes;
-                if (pp.stages > 4) pp.stages = 4;
-                smem = res + pp.stages * kHaloBytes + GemmCfg<64>::kExtraBytes + bias_bytes;
+        // shared-memory plan for a weight K block of `b_bytes` per CTA (pair mode: half of BN rows)
+        struct Plan { int halo, resb, b_stages, stages, smem; };
+        auto plan = [&](int b_bytes) {
+            Plan r;
+            const int res = (pp.kb_end - pp.kb_begin) * b_bytes;
+            if (pp.halo && pp.raw == 0) {
+                r.halo = 1;
+                r.resb = (h->resident_b && pp.tiles_n == 1 && res + 2 * kHaloBytes <= budget) ? 1 : 0;
+                if (r.resb) {
+                    r.b_stages = 0;
+                    r.stages = (budget - res) / kHaloBytes;
+                    if (r.stages > 4) r.stages = 4;
+                    r.smem = res + r.stages * kHaloBytes + GemmCfg<64>::kExtraBytes + bias_bytes;
+                } else {
+                    r.b_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+                    r.stages = (budget - r.b_stages * b_bytes) / kHaloBytes;
+                    if (r.stages > 4) r.stages = 4;
+                    r.smem = r.stages * kHaloBytes + r.b_stages * b_bytes + GemmCfg<64>::kExtraBytes + bias_bytes;
+                }
             } else {
-                pp.b_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-                pp.stages = (budget - pp.b_stages * b_bytes) / kHaloBytes;
-                if (pp.stages > 4) pp.stages = 4;
-                smem = pp.stages * kHaloBytes + pp.b_stages * b_bytes + GemmCfg<64>::kExtraBytes + bias_bytes;
+                r.halo = 0;
+                r.resb = 0;
+                r.b_stages = 0;
+                r.stages = budget / (kABytes + b_bytes);
+                if (r.stages > 8) r.stages = 8;
+                if (r.stages < 2) r.stages = 2;
+                r.smem = r.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes + bias_bytes;
             }
-        } else {
-            pp.halo = 0;
-            pp.resb = 0;
-            pp.stages = budget / (kABytes + b_bytes);
-            if (pp.stages > 8) pp.stages = 8;
-            if (pp.stages < 2) pp.stages = 2;
-            smem = pp.stages * (kABytes + b_bytes) + GemmCfg<64>::kExtraBytes + bias_bytes;
-        }
-        const int smem_plain = smem, stages_plain = pp.stages;
-        int smem_pair = smem, stages_pair = pp.stages;       // pair mode keeps only half of the weight tile per CTA
-        if (!pp.halo) {
-            stages_pair = budget / (kABytes + b_bytes / 2);
-            if (stages_pair > 8) stages_pair = 8;
-            smem_pair = stages_pair * (kABytes + b_bytes / 2) + GemmCfg<64>::kExtraBytes + bias_bytes;
-        }
+            return r;
+        };
+        auto apply = [&](const Plan& r) { pp.halo = r.halo; pp.resb = r.resb; pp.b_stages = r.b_stages; pp.stages = r.stages; };
+        const int b_full = BN * kBlockK * 2;
+        const Plan plain = plan(b_full), pair = plan(b_full / 2);
+        apply(plain);
+        int smem = plain.smem;
         // cluster mode (plain single-pass layers): CTA pairs share every weight tile through TMA multicast, which
         // halves the L2 -> SM weight traffic of the layers whose operand fetch, not the MMA, limits them
         pp.cluster = 1;
@@ -873,12 +903,13 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         const int pair_units = ((num_m + cs - 1) / cs) * pp.tiles_n;
         // gemm_cluster = 1: when every CTA pair gets work; 2 (tests): whenever the layer has two M tiles;
         // 3: only layers with many M tiles per CTA
-        if (h->gemm_cluster && !pp.halo && pp.raw == 0 && npass == 1 && num_m >= 2 &&
+        const bool pair_mode = h->gemm_twocta && cs == 2;
+        if (h->gemm_cluster && (!pp.halo || (pair_mode && h->gemm_pair_halo)) && pp.raw == 0 && npass == 1 && num_m >= 2 &&
             (h->gemm_cluster == 2 || (h->gemm_cluster == 1 && pair_units >= h->sm_count / cs) ||
              (h->gemm_cluster == 3 && num_m >= 2 * h->sm_count))) {
             pp.cluster = cs;
             pp.num_units = pair_units;
-            if (h->gemm_twocta && cs == 2) { pp.twocta = 1; pp.stages = stages_pair; smem = smem_pair; }
+            if (pair_mode) { pp.twocta = 1; apply(pair); smem = pair.smem; }
             g = cs * (h->sm_count / cs);
             if (encode_weight_map(&pp.tmBh, L.w_hi, L.K, L.N, BN / cs) != FADB_OK) { pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; }
         }
@@ -912,7 +943,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                 // no answer, or clusters would leave more than a tenth of the SMs idle: plain launch
                 (void)cudaGetLastError();
                 pp.cluster = 1;
-                if (pp.twocta) { pp.twocta = 0; pp.stages = stages_plain; cfg.dynamicSmemBytes = (size_t)smem_plain; kern = kern_plain; }
+                if (pp.twocta) { pp.twocta = 0; apply(plain); cfg.dynamicSmemBytes = (size_t)plain.smem; kern = kern_plain; }
                 pp.num_units = pp.num_tiles;
                 attr[0].val.clusterDim.x = 1;
                 cfg.gridDim = dim3((unsigned)grid);
