@@ -143,7 +143,10 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics, like the local arrive: the state being handed over is tensor memory, ordered by the tcgen05
+    // fences, not global memory (an explicit .release.cluster compiled to MEMBAR.ALL.GPU + ERRBAR: 20 % of the
+    // epilogue's stall samples in the first pair-mode profile)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion is signalled on a barrier that may live in the peer CTA (the pair's leader)
 __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
