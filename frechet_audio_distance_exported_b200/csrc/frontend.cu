@@ -143,10 +143,11 @@ __device__ __forceinline__ void build_pass_twiddles(double2* __restrict__ ptw, c
 
 // One in-place Stockham pass of radix R over the warp's M-point buffer: every lane first pulls ALL of
 // its butterfly inputs into registers, the warp syncs, then the outputs go back to the same buffer.
-// The FIRST pass takes its inputs from `load(n)` (windowed PCM straight from global memory) instead.
-template <int M, int R, bool FIRST, class Load>
+// The FIRST pass takes its inputs from registers instead: z[j] = input element lane + 32 j (windowed PCM straight from
+// global memory).
+template <int M, int R, bool FIRST>
 __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ ptw, int pp, int lane,
-                                         const Load& load) {
+                                         const double2 (&z)[M / 32]) {
     constexpr int T = M / R;                 // butterflies in the pass
     constexpr int PER = (T + 31) / 32;       // per lane
     double2 u[PER][R];
@@ -158,7 +159,7 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
             for (int r = 0; r < R; ++r) {
                 double2 v;
                 if (FIRST) {
-                    v = load(i + r * T);
+                    v = z[q + r * PER];               // element i + r T = lane + 32 (q + r PER)
                 } else {
                     v = x[pidx(i + r * T)];
                     if (r > 0) v = cmul(v, ptw[(q * (R - 1) + (r - 1)) * 32 + lane]);
@@ -213,16 +214,18 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
     __syncwarp();
 }
 
-// complex FFT of length M (128 / 256 / 512) of the sequence load(0..M-1), result in x (padded index pidx)
-template <int M, class Load>
+// complex FFT of length M (128 / 256 / 512) of the sequence held as z[j] = element lane + 32 j, result in x (padded
+// index pidx)
+template <int M>
 __device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ ptw, int lane,
-                                            const Load& load) {
+                                            const double2 (&z)[M / 32]) {
     using P = FftPlan<M>;
     constexpr int R0 = P::radix(0), R1 = P::radix(1), R2 = P::radix(2);
-    fft_pass<M, R0, true>(x, ptw, 1, lane, load);
-    fft_pass<M, R1, false>(x, ptw + P::offset(1) * 32, R0, lane, load);
-    fft_pass<M, R2, false>(x, ptw + P::offset(2) * 32, R0 * R1, lane, load);
-    if constexpr (P::kNumPasses == 4) fft_pass<M, P::radix(3), false>(x, ptw + P::offset(3) * 32, R0 * R1 * R2, lane, load);
+    static_assert(M / P::radix(0) >= 32, "first pass: at least one butterfly per lane");
+    fft_pass<M, R0, true>(x, ptw, 1, lane, z);
+    fft_pass<M, R1, false>(x, ptw + P::offset(1) * 32, R0, lane, z);
+    fft_pass<M, R2, false>(x, ptw + P::offset(2) * 32, R0 * R1, lane, z);
+    if constexpr (P::kNumPasses == 4) fft_pass<M, P::radix(3), false>(x, ptw + P::offset(3) * 32, R0 * R1 * R2, lane, z);
 }
 
 constexpr int kFrontWarps = 8;
@@ -263,42 +266,63 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView
         if (nb >= 0 && nb < (long long)p.n_samples && nb < f0 + p.hop + p.win_len + (128 / pcm.sample_bytes()))
             prefetch_l1(pcm.addr(nb));
     }
-    // the loader hands z[n] to the first FFT pass in registers: the windowed frame never makes its own round
-    // trip through shared memory
-    auto load_z = [&](int n) -> double2 {
-        float s0 = 0.f, s1 = 0.f;
-        if (2 * n < p.win_len) {
-            if (pair_ok) {
-                const float2 t = pcm.pair(f0 + 2 * n);
-                s0 = t.x; s1 = t.y;
-            } else if (interior) {
-                s0 = pcm[f0 + 2 * n];
-                s1 = (2 * n + 1 < p.win_len) ? pcm[f0 + 2 * n + 1] : 0.f;
-            } else {
+    // The windowed frame goes to the first FFT pass in registers (no round trip through shared memory).  The common
+    // case is a branch-free block of predicated 8-byte loads, so all of a frame's loads are in flight together; the
+    // first version decided per element and serialised eight load -> convert round trips (20 % of the stall samples
+    // of this phase sat on the first conversion after each load).
+    constexpr int J = M / 32;
+    float2 raw[J];
+    if (pair_ok) {
+        if (pcm.s) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 2 * n + e;
-                    float s = 0.f;
-                    if (j < p.win_len) {
-                        long long src = f0 + j;
-                        if (p.centered) {        // np.pad(mode='reflect'): edge sample not repeated
-                            if (src < 0) src = -src;
-                            if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
-                        }
-                        if (src >= 0 && src < p.n_samples) s = pcm[src];
-                    }
-                    if (e == 0) s0 = s; else s1 = s;
-                }
+            for (int j = 0; j < J; ++j) {
+                const int n = lane + 32 * j;
+                short2 v = make_short2(0, 0);
+                if (2 * n < p.win_len) v = __ldg(reinterpret_cast<const short2*>(pcm.s + f0 + 2 * n));
+                raw[j] = make_float2((float)v.x * 3.0517578125e-05f, (float)v.y * 3.0517578125e-05f);
             }
-            if (p.quantize) {                    // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
-                s0 = __fdiv_rn(truncf(__fmul_rn(s0, 32767.0f)), 32767.0f);
-                s1 = __fdiv_rn(truncf(__fmul_rn(s1, 32767.0f)), 32767.0f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int n = lane + 32 * j;
+                raw[j] = make_float2(0.f, 0.f);
+                if (2 * n < p.win_len) raw[j] = __ldg(reinterpret_cast<const float2*>(pcm.f + f0 + 2 * n));
             }
         }
-        const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * n]);
-        return make_double2((double)s0 * wn.x, (double)s1 * wn.y);
-    };
-    fft_inplace<M>(x, s_ptw, lane, load_z);
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {            // frame edges (reflect padding, clip ends) and odd alignments
+            const int n = lane + 32 * j;
+            float s01[2] = {0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = 2 * n + e;
+                if (i < p.win_len) {
+                    long long src = f0 + i;
+                    if (p.centered) {            // np.pad(mode='reflect'): edge sample not repeated
+                        if (src < 0) src = -src;
+                        if (src >= p.logical_len) src = 2LL * (p.logical_len - 1) - src;
+                    }
+                    if (src >= 0 && src < p.n_samples) s01[e] = pcm[src];
+                }
+            }
+            raw[j] = make_float2(s01[0], s01[1]);
+        }
+    }
+    if (p.quantize) {                            // clap.py:70-72: (x*32767).astype(int16)/32767, trunc toward 0
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            raw[j].x = __fdiv_rn(truncf(__fmul_rn(raw[j].x, 32767.0f)), 32767.0f);
+            raw[j].y = __fdiv_rn(truncf(__fmul_rn(raw[j].y, 32767.0f)), 32767.0f);
+        }
+    }
+    double2 z[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {                // fp32 PCM x fp64 Hann, like numpy's promotion (s_win is 0 past win_len)
+        const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * (lane + 32 * j)]);
+        z[j] = make_double2((double)raw[j].x * wn.x, (double)raw[j].y * wn.y);
+    }
+    fft_inplace<M>(x, s_ptw, lane, z);
 
     // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32.
     // Bins k and M-k come from the same pair (Z[k], Z[M-k]): X[k] = ze + w_k zo, X[M-k] = conj(ze - w_k zo), so each
