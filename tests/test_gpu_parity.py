@@ -87,6 +87,38 @@ def test_tcgen05_layer_matches_conv2d(eng_vgg, prec, case):
     assert relerr(out, ref) < (2e-5 if prec == "bf16" else 1e-4)
 
 
+PAIR_MODES = {
+    "cta_group2": {"FADB_CLUSTER": "2"},                                  # one M = 256 MMA per CTA pair (the default at scale)
+    "multicast": {"FADB_CLUSTER": "2", "FADB_TWOCTA": "0"},               # two M = 128 MMAs, weight tile multicast
+    "cta_group2_halo": {"FADB_CLUSTER": "2", "FADB_PAIR_HALO": "1"},      # pairs on the halo-mode layers too
+}
+
+
+@pytest.mark.parametrize("mode", sorted(PAIR_MODES))
+def test_cta_pair_modes_match_plain_launch(vgg_sd, monkeypatch, mode):
+    """The cluster launches only trigger on layers with at least 74 work units, which none of the small cases above
+    has; FADB_CLUSTER=2 forces them.  Every pair variant must reproduce the plain single-CTA kernel (same K order per
+    output row), on every layer geometry incl. odd M-tile counts (the trailing tile of a pair runs on zero-filled
+    boxes), and through the whole VGGish network."""
+    from frechet_audio_distance_exported_b200 import Engine
+    monkeypatch.setenv("FADB_CLUSTER", "0")
+    plain = Engine("vggish", vgg_sd, precision="bf16")
+    for k, v in PAIR_MODES[mode].items():
+        monkeypatch.setenv(k, v)
+    paired = Engine("vggish", vgg_sd, precision="bf16")                  # the switches are read when the handle is created
+    for case in CONV_CASES:
+        B, H, W, Cin, Cout, k, relu, pool = case
+        g = torch.Generator().manual_seed(hash(case) % 1000)
+        x = torch.randn((B, H, W, Cin), generator=g).cuda()
+        w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5).cuda()
+        b = (torch.randn(Cout, generator=g) * 0.1).cuda()
+        a = plain.debug_conv_layer(x, w, b, k, bool(relu), pool).cpu().numpy()
+        c = paired.debug_conv_layer(x, w, b, k, bool(relu), pool).cpu().numpy()
+        assert relerr(c, a) < 1e-6, (mode, case)
+    feats = torch.randn(37, 96, 64, generator=torch.Generator().manual_seed(5)).cuda() * 2.0
+    assert relerr(paired.embed_features(feats).cpu().numpy(), plain.embed_features(feats).cpu().numpy()) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ front ends
 def test_vggish_frontend_golden(eng_vgg, golden):
     z = golden("vggish_frontend.npz")
