@@ -30,6 +30,7 @@ SYMBOLS = [
     ("fadb_frontend", C.c_int, [_vp, C.c_int, _fp, _i64, _i64, _i64, _fp, _vp]),
     ("fadb_embed_dim", C.c_int, [C.c_int]),
     ("fadb_embed", C.c_int, [_vp, _fp, _i64, _i64, _fp, _vp]),
+    ("fadb_resample", C.c_int, [_vp, _fp, _i64, _i64, _i64, C.c_double, _dp, C.c_int, C.c_int, _fp, _i64, _i64, _vp]),
     ("fadb_embed_pcm", C.c_int, [_vp, _fp, _i64, _i64, _i64, _fp, _vp]),
     ("fadb_embed_pcm16", C.c_int, [_vp, _vp, _i64, _i64, _i64, _fp, _vp]),
     ("fadb_stats_accumulate", C.c_int, [_vp, _fp, _i64, C.c_int, _i64, _dp, _dp, _vp]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfadb200.so")
 STAMP = os.path.join(HERE, "libfadb200.so.stamp")
-SOURCES = ["api.cu", "gemm_tc.cu", "conv1.cu", "pack.cu", "frontend.cu", "stats.cu", "frechet.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "conv1.cu", "pack.cu", "frontend.cu", "stats.cu", "frechet.cu", "resample.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -561,6 +561,20 @@ int fadb_frontend(fadb_handle* h, int model, const float* pcm_dev, int64_t n_cli
     return FADB_OK;
 }
 
+int fadb_resample(fadb_handle* h, const float* in_dev, int64_t n_clips, int64_t n_in, int64_t in_stride, double ratio,
+                  const double* win_dev, int nwin, int num_table, float* out_dev, int64_t n_out, int64_t out_stride,
+                  void* stream) {
+    if (!h || !in_dev || !win_dev || !out_dev) { set_error("fadb_resample: NULL argument"); return FADB_E_INVALID; }
+    if (n_in <= 0 || n_out != (int64_t)((double)n_in * ratio)) {
+        set_error("fadb_resample: n_out must be int(n_in * ratio) (resampy semantics), got %lld for %lld x %g",
+                  (long long)n_out, (long long)n_in, ratio);
+        return FADB_E_INVALID;
+    }
+    cudaSetDevice(h->device);
+    return launch_resample(h, in_dev, n_clips, n_in, in_stride, ratio, win_dev, nwin, num_table, out_dev, n_out, out_stride,
+                           (cudaStream_t)stream);
+}
+
 int fadb_embed_dim(int model) { return embed_dim(model); }
 
 int fadb_embed(fadb_handle* h, const float* feats_dev, int64_t n_items, int64_t t_frames, float* emb_dev, void* stream) {

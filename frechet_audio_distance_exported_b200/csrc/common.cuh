@@ -158,6 +158,11 @@ int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64
 
 int64_t frontend_rows(int model, int64_t n_samples);
 
+// resample.cu
+int launch_resample(fadb_handle* h, const float* in, int64_t n_clips, int64_t n_in, int64_t in_stride, double ratio,
+                    const double* win, int nwin, int num_table, float* out, int64_t n_out, int64_t out_stride,
+                    cudaStream_t st);
+
 // conv1.cu — Cin = 1 direct 3x3 conv on CUDA cores
 int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, __nv_bfloat16* out_hi,
                         __nv_bfloat16* out_lo, cudaStream_t st);

@@ -114,6 +114,29 @@ class Engine:
             check(fn(self.h, _p(pcm), n_clips, n, pcm.stride(0), _p(out), C.c_void_p(_stream_ptr())))
         return out
 
+    def resample(self, pcm: torch.Tensor, sr_orig: int, sr_new: int) -> torch.Tensor:
+        """pcm [n_clips, n] fp32 cuda at sr_orig -> [n_clips, int(n * sr_new / sr_orig)] fp32 at sr_new, with the
+        semantics (and the exact fp64 arithmetic) of resample.resample / resampy kaiser_best."""
+        from .resample import filter_table
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.dim() == 2 and pcm.stride(1) == 1
+        key = (int(sr_orig), int(sr_new))
+        if not hasattr(self, "_resample_tables"):
+            self._resample_tables = {}
+        if key not in self._resample_tables:
+            win, num_table, ratio = filter_table(*key)
+            self._resample_tables[key] = (torch.from_numpy(win).to(self.device), num_table, ratio)
+        win_dev, num_table, ratio = self._resample_tables[key]
+        n_clips, n = pcm.shape
+        n_out = int(n * ratio)
+        if n_out < 1:
+            raise ValueError(f"Input signal length={n} is too small to resample from {sr_orig}->{sr_new}")
+        out = torch.empty((n_clips, n_out), dtype=torch.float32, device=pcm.device)
+        if n_clips:
+            check(self.lib.fadb_resample(self.h, _p(pcm), n_clips, n, pcm.stride(0), C.c_double(ratio), _p(win_dev),
+                                         win_dev.numel(), num_table, _p(out), n_out, out.stride(0),
+                                         C.c_void_p(_stream_ptr())))
+        return out
+
     # ------------------------------------------------------------------ statistics
     def new_acc(self, d: Optional[int] = None) -> torch.Tensor:
         d = self.dim if d is None else d

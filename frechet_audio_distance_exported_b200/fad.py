@@ -201,7 +201,18 @@ class FrechetAudioDistance:
         self.model = _B200Model(self.engine)
 
     # ------------------------------------------------------------------ fad.py:302-408
-    def _prepare_clip(self, audio: np.ndarray, sr: int) -> np.ndarray:
+    def _check_length(self, n: int) -> None:
+        """length limits at the model's own sample rate (after any resampling)"""
+        if self.model_name == "clap" and n > 480000:
+            raise ValueError("CLAP clips are limited to 10 s")
+        if self.model_name != "vggish" and self.model_name != "clap":
+            n_fft = {8000: 256, 16000: 512, 32000: 1024}[self.sample_rate]
+            if n <= n_fft // 2:
+                raise ValueError("clip too short for reflect padding")
+
+    def _prepare_clip(self, audio: np.ndarray, sr: int, device_resample: bool = False) -> np.ndarray:
+        """Host part of vggish.py:241-250 / pann.py:93-101: mono mix, then resampling to the model's rate — on the
+        host, or left to the GPU (`device_resample`: the clip comes back at its own rate, float32)."""
         audio = np.asarray(audio)
         raw16 = audio.dtype == np.int16 and audio.ndim == 1 and sr == self.sample_rate
         if audio.dtype == np.int16 and not raw16:                              # raw PCM16 that needs host-side work first
@@ -209,24 +220,28 @@ class FrechetAudioDistance:
         if audio.ndim > 1:                                                     # vggish.py:245-246 / pann.py:96-97
             audio = np.mean(audio, axis=1)
         if sr != self.sample_rate:                                             # vggish.py:249-250 / pann.py:100-101
+            if device_resample:
+                n_out = int(audio.shape[0] * (float(self.sample_rate) / float(sr)))
+                if n_out < 1:
+                    raise ValueError(f"Input signal length={audio.shape[0]} is too small to resample from "
+                                     f"{sr}->{self.sample_rate}")
+                self._check_length(n_out)
+                return np.ascontiguousarray(audio, dtype=np.float32)
             audio = resample(audio, sr, self.sample_rate)
         # mono native-rate int16 PCM goes to the device as is (half the bytes); the front end divides by 32768
         audio = np.ascontiguousarray(audio, dtype=np.int16 if raw16 else np.float32)
-        if self.model_name == "clap" and audio.shape[0] > 480000:
-            raise ValueError("CLAP clips are limited to 10 s")
-        if self.model_name != "vggish" and self.model_name != "clap":
-            n_fft = {8000: 256, 16000: 512, 32000: 1024}[self.sample_rate]
-            if audio.shape[0] <= n_fft // 2:
-                raise ValueError("clip too short for reflect padding")
+        self._check_length(audio.shape[0])
         return audio
 
     def get_embeddings(self, x: List[np.ndarray], sr: int) -> np.ndarray:
         """Embeddings for a list of clips, concatenated in input order.  Clips of equal length are
-        batched into one device call (the reference loops clip by clip, fad.py:317)."""
+        batched into one device call (the reference loops clip by clip, fad.py:317); clips at another sample
+        rate are resampled on the GPU (`fadb_resample`, same arithmetic as resample.py)."""
+        on_device = sr != self.sample_rate
         prepared = []
         for audio in x:
             try:
-                prepared.append(self._prepare_clip(audio, sr))
+                prepared.append(self._prepare_clip(audio, sr, device_resample=on_device))
             except Exception as e:                                             # fad.py:400-403
                 if self.verbose:
                     print(f"[Exported FAD] Error processing audio: {e}")
@@ -238,13 +253,16 @@ class FrechetAudioDistance:
         results: Dict[int, np.ndarray] = {}
         for (n, _), idxs in by_len.items():
             try:
-                rows = self.engine.frontend_rows(n) if self.model_name == "vggish" else 1
+                n_model = int(n * (float(self.sample_rate) / float(sr))) if on_device else n
+                rows = self.engine.frontend_rows(n_model) if self.model_name == "vggish" else 1
                 if rows <= 0:
                     for i in idxs:
                         results[i] = np.zeros((0, self.engine.dim), dtype=np.float32)
                     continue
-                host = torch.from_numpy(np.stack([prepared[i] for i in idxs]))
-                emb = self.engine.embed_pcm(host.to(self.device, non_blocking=False)).cpu().numpy()
+                pcm = torch.from_numpy(np.stack([prepared[i] for i in idxs])).to(self.device, non_blocking=False)
+                if on_device:
+                    pcm = self.engine.resample(pcm, sr, self.sample_rate)
+                emb = self.engine.embed_pcm(pcm).cpu().numpy()
                 for j, i in enumerate(idxs):
                     results[i] = emb[j * rows:(j + 1) * rows]
             except Exception as e:

@@ -8,8 +8,9 @@ sinc table with 64 zero crossings, 512 table entries per crossing, roll-off 0.94
 int(n * ratio)).  PARITY UNPINNED: it cannot be checked against resampy offline; tests pin the properties the
 reference's own tests pin (output length, tests/test_basic.py:212-228) plus signal-level sanity.
 
-Host-side NumPy: resampling belongs to file ingestion (the reference does it on the host too), not to the
-B200 hot path, which only ever sees native-rate PCM.
+`resample` is the host (NumPy) form, used by `load_audio`.  Clips handed to `get_embeddings` at another rate are
+resampled on the GPU by `fadb_resample` (csrc/resample.cu), which replays exactly this arithmetic in fp64 and agrees
+with this function bit for bit; `filter_table` builds the interpolation table it takes.
 """
 from __future__ import annotations
 
@@ -30,6 +31,17 @@ def _kaiser_best():
     sinc_win = _ROLLOFF * np.sinc(_ROLLOFF * np.linspace(0, _NUM_ZEROS, num=n + 1, endpoint=True))
     taper = np.kaiser(2 * n + 1, _BETA)[n:]
     return taper * sinc_win, num_table
+
+
+def filter_table(sr_orig: int, sr_new: int):
+    """-> (right wing of the interpolation filter as float64, scaled by the ratio when downsampling; table entries per
+    zero crossing; ratio) — the arguments of the C entry point `fadb_resample`."""
+    ratio = float(sr_new) / float(sr_orig)
+    win, num_table = _kaiser_best()
+    win = win.copy()
+    if ratio < 1:
+        win *= ratio
+    return win, num_table, ratio
 
 
 def resample(x: np.ndarray, sr_orig: int, sr_new: int) -> np.ndarray:

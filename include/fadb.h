@@ -108,6 +108,16 @@ int fadb_embed_pcm(fadb_handle* h, const float* pcm_dev, int64_t n_clips, int64_
 int fadb_embed_pcm16(fadb_handle* h, const int16_t* pcm_dev, int64_t n_clips, int64_t n_samples,
                      int64_t pcm_stride, float* emb_dev, void* stream);
 
+/* ---------------------------------------------------------------- resampling
+ * resampy.resample(x, sr_orig, sr_new) semantics (filter kaiser_best) for clips already on the device; replaces
+ * fad.py:159, models/vggish.py:250, models/pann.py:101.  ratio = sr_new / sr_orig, n_out = int(n_in * ratio).
+ * win_dev: the interpolation filter's right wing, double[nwin], with num_table entries per zero crossing, already
+ * multiplied by ratio when ratio < 1 (frechet_audio_distance_exported_b200/resample.py builds it); the kernel replays
+ * resample.py's fp64 arithmetic operation by operation.  Parity against resampy itself is unpinned (not installable). */
+int fadb_resample(fadb_handle* h, const float* in_dev, int64_t n_clips, int64_t n_in, int64_t in_stride, double ratio,
+                  const double* win_dev, int nwin, int num_table, float* out_dev, int64_t n_out, int64_t out_stride,
+                  void* stream);
+
 /* ---------------------------------------------------------------- statistics
  * Replaces calculate_embd_statistics, fad.py:483-496, as a summable sufficient statistic.
  *   acc_dev : double[1 + d + d*d] = { n, sum(x-K), sum (x-K)(x-K)^T }   (caller zero-initialises)

@@ -71,7 +71,11 @@ def test_get_embeddings_semantics(fad_vgg):
     assert np.max(np.abs(out[:3] - ref)) / np.max(np.abs(ref)) < 1e-2
     assert fad_vgg.get_embeddings([], 16000).shape == (0,)
     long44 = synth.sine_clip(3.0, 440.0, 44100)                            # 44.1 kHz input is resampled (vggish.py:249-250)
-    assert fad_vgg.get_embeddings([long44], 44100).shape == (3, 128)
+    e44 = fad_vgg.get_embeddings([long44], 44100)                          # resampled on the GPU (fadb_resample)
+    assert e44.shape == (3, 128)
+    from frechet_audio_distance_exported_b200.resample import resample
+    assert np.array_equal(e44, fad_vgg.get_embeddings([resample(long44, 44100, 16000)], 16000))   # == host resampling
+    assert fad_vgg.get_embeddings([long44[:10]], 44100).shape == (0, 128)  # too short for one patch after resampling
     assert fad_vgg._get_embedding_for_audio(a).shape == (2, 128)
 
 

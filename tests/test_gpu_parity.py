@@ -392,3 +392,23 @@ def test_pcm16_host_paths(vgg_sd):
     out = fad.get_embeddings([qb[0], fb[1], qb[2][:16400]], 16000)
     assert out.shape == (2 + 2 + 1, 128)
     assert np.array_equal(out[:2], eb[:2]) and np.array_equal(out[2:4], eb[2:4])
+
+
+@pytest.mark.parametrize("sr_in,sr_out,n", [(44100, 16000, 44100), (8000, 16000, 12000), (48000, 32000, 50001),
+                                            (22050, 16000, 3000), (16000, 8000, 777)])
+def test_device_resampler_equals_host_restatement(eng_vgg, sr_in, sr_out, n):
+    """fadb_resample replays resample.py (resampy kaiser_best semantics; parity against resampy itself is unpinned, it
+    is not installable here) operation by operation in fp64: identical output samples, output length int(n * ratio)
+    (reference tests/test_basic.py:212-228 pins the length)."""
+    from frechet_audio_distance_exported_b200.resample import resample
+    t = np.arange(n) / sr_in
+    clips = np.stack([(0.5 * np.sin(2 * np.pi * f * t) + 0.05 * synth.background_clip(i, n)).astype(np.float32)
+                      for i, f in enumerate((440.0, 3000.0, 60.0))])
+    out = eng_vgg.resample(torch.from_numpy(clips).cuda(), sr_in, sr_out).cpu().numpy()
+    ref = np.stack([resample(c, sr_in, sr_out) for c in clips])
+    assert out.shape == ref.shape == (3, int(n * (float(sr_out) / float(sr_in)))) and out.dtype == np.float32
+    assert np.array_equal(out, ref)
+    # a strided view (row stride > length) gives the same samples
+    wide = torch.zeros((3, n + 5), dtype=torch.float32, device="cuda")
+    wide[:, :n] = torch.from_numpy(clips).cuda()
+    assert np.array_equal(eng_vgg.resample(wide[:, :n], sr_in, sr_out).cpu().numpy(), ref)
