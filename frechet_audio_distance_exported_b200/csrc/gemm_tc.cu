@@ -11,14 +11,19 @@
 //     tile per (tap, channel block); the 3x3 halo and the zero padding come for free from TMA
 //     out-of-bounds zero fill (coordinates start at x0-1 / y0-1).  No im2col buffer exists.
 //   * B operand: packed weights [Cout][tap][Cin] bf16 (K-major), 2-D tensor map, box (64, BN).
-//   * MMA: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN (64/128/256), K = 16, fp32
-//     accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the
-//     MMAs of tile i+1.
+//   * MMA: tcgen05.mma.kind::f16, N = BN (64/128/256), K = 16, fp32 accumulators in TMEM, double-buffered
+//     (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.  Large plain layers run as
+//     CLUSTERS OF TWO CTAs: one cta_group::2 MMA (M = 256, 128 rows per SM) per K step issued by the leader,
+//     each CTA holding its own A tile and half of the weight tile (PAIR instantiation; FADB_TWOCTA=0 selects
+//     the older variant: two M = 128 MMAs with the weight tile multicast).  Everything else is cta_group::1.
+//   * Halo mode (3x3 layers on maps >= 8 wide, >= 16 high): ONE 10 x 18-pixel activation box per channel block
+//     serves all nine taps as shifted descriptor views; weights stream through their own ring (warp 3) or stay
+//     resident in shared memory.
 //   * split-bf16 ("bf16x3") mode: the K loop runs three passes (A_hi*B_hi, A_lo*B_hi, A_hi*B_lo)
 //     into the same accumulator, giving ~2^-16 relative operand precision with the same kernel.
-//   * Epilogue (8 warps): tcgen05.ld -> +bias (folded BN) -> ReLU -> optional 2x2 max / avg pool done with
-//     two warp shuffles per value (the pooled layers use boxes <= 16 pixels wide, so a pooling window
-//     lives inside one warp) -> bf16 hi(/lo) or fp32 NHWC, 16-byte stores straight from registers.
+//   * Epilogue (8 warps): tcgen05.ld -> +bias (folded BN, staged in shared memory) -> ReLU -> optional 2x2 max /
+//     avg pool as a channel-splitting shuffle butterfly (the pooled layers use boxes <= 16 pixels wide, so a
+//     pooling window lives inside one warp) -> bf16 hi(/lo) or fp32 NHWC, 16-byte stores straight from registers.
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = weight
 // producer in halo mode, warps 4..11 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter).
