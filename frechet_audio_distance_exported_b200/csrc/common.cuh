@@ -100,7 +100,7 @@ struct fadb_handle {
     int resident_b = 1;             // keep short-K weight slabs resident in smem (see gemm_tc.cu)
     int gemm_cluster = 1;           // 1 = CTA clusters share weight tiles through TMA multicast (plain single-pass layers)
     int gemm_cluster_size = 2;      // CTAs per cluster: 2 or 4
-    int gemm_pair_halo = 0;         // CTA pairs for the halo-mode layers too: works, but measured 3-5 % slower (short tiles)
+    int gemm_pair_halo = 1;         // CTA pairs for the halo-mode layers too (CNN14 blocks 1-4: +10 %)
     int gemm_twocta = 1;            // clusters of 2: 1 = cta_group::2 MMAs (M = 256 across the pair) instead of weight multicast
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;
