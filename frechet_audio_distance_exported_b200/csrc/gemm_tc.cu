@@ -939,9 +939,22 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         if (pp.cluster > 1) {
             // a persistent kernel wants every cluster co-resident: size the grid to what fits (a GPC with an odd
             // number of free SMs leaves one without a partner)
-            int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess &&
-                nclusters * pp.cluster * 10 >= h->sm_count * 9) {
+            // (the answer depends only on the kernel, the cluster size and the shared-memory size: cache it, the query
+            // costs tens of microseconds per launch)
+            struct Occ { const void* k; int device, cluster, smem, n; };
+            static thread_local Occ occ_cache[16];
+            static thread_local int occ_used = 0;
+            int nclusters = -1;
+            for (int i = 0; i < occ_used; ++i)
+                if (occ_cache[i].k == (const void*)kern && occ_cache[i].device == h->device && occ_cache[i].cluster == pp.cluster &&
+                    occ_cache[i].smem == smem)
+                    nclusters = occ_cache[i].n;
+            if (nclusters < 0) {
+                nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess) { nclusters = 0; (void)cudaGetLastError(); }
+                if (occ_used < 16) occ_cache[occ_used++] = Occ{(const void*)kern, h->device, pp.cluster, smem, nclusters};
+            }
+            if (nclusters * pp.cluster * 10 >= h->sm_count * 9) {
                 if (nclusters > pp.num_units) nclusters = pp.num_units;
                 cfg.gridDim = dim3((unsigned)(pp.cluster * nclusters));
             } else {
