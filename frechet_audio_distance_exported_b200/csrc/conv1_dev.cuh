@@ -28,22 +28,25 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
     return d;
 }
 
+// one 32-byte global store (256-bit LSU access of sm_100): 16 bf16 channels = one full sector per instruction
+__device__ __forceinline__ void st256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 __device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi, __nv_bfloat16* lo, size_t o) {
     uint4 a, b;
     a.x = pack2(v[0], v[1]); a.y = pack2(v[2], v[3]); a.z = pack2(v[4], v[5]); a.w = pack2(v[6], v[7]);
     b.x = pack2(v[8], v[9]); b.y = pack2(v[10], v[11]); b.z = pack2(v[12], v[13]); b.w = pack2(v[14], v[15]);
-    uint4* d = reinterpret_cast<uint4*>(hi + o);
-    d[0] = a;
-    d[1] = b;
+    st256(hi + o, a, b);
     if (lo) {
         float r[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = v[j] - bfr(v[j]);
         a.x = pack2(r[0], r[1]); a.y = pack2(r[2], r[3]); a.z = pack2(r[4], r[5]); a.w = pack2(r[6], r[7]);
         b.x = pack2(r[8], r[9]); b.y = pack2(r[10], r[11]); b.z = pack2(r[12], r[13]); b.w = pack2(r[14], r[15]);
-        uint4* e = reinterpret_cast<uint4*>(lo + o);
-        e[0] = a;
-        e[1] = b;
+        st256(lo + o, a, b);
     }
 }
 

@@ -586,9 +586,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                     h0.z = pack_bf16x2(g[4], g[5]); h0.w = pack_bf16x2(g[6], g[7]);
                     h1.x = pack_bf16x2(g[8], g[9]); h1.y = pack_bf16x2(g[10], g[11]);
                     h1.z = pack_bf16x2(g[12], g[13]); h1.w = pack_bf16x2(g[14], g[15]);
-                    uint4* d = reinterpret_cast<uint4*>(out_hi + obase + sub * 16);
-                    d[0] = h0;
-                    d[1] = h1;
+                    st_global_256(out_hi + obase + sub * 16, h0, h1);
                     if (out_lo) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) g[j] -= bf16_round(g[j]);
@@ -596,9 +594,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                         h0.z = pack_bf16x2(g[4], g[5]); h0.w = pack_bf16x2(g[6], g[7]);
                         h1.x = pack_bf16x2(g[8], g[9]); h1.y = pack_bf16x2(g[10], g[11]);
                         h1.z = pack_bf16x2(g[12], g[13]); h1.w = pack_bf16x2(g[14], g[15]);
-                        uint4* e = reinterpret_cast<uint4*>(out_lo + obase + sub * 16);
-                        e[0] = h0;
-                        e[1] = h1;
+                        st_global_256(out_lo + obase + sub * 16, h0, h1);
                     }
                 }
             }

@@ -567,9 +567,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     if (valid) {
                         const size_t o = obase + c * 32 + (odd ? 16 : 0) + (up ? 8 : 0);
                         if (p.out_f32) {
-                            float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
-                            d[0] = make_float4(g8[0], g8[1], g8[2], g8[3]);
-                            d[1] = make_float4(g8[4], g8[5], g8[6], g8[7]);
+                            st_global_256(p.out_f32 + o,
+                                          make_uint4(__float_as_uint(g8[0]), __float_as_uint(g8[1]), __float_as_uint(g8[2]),
+                                                     __float_as_uint(g8[3])),
+                                          make_uint4(__float_as_uint(g8[4]), __float_as_uint(g8[5]), __float_as_uint(g8[6]),
+                                                     __float_as_uint(g8[7])));
                         } else {
                             uint4 hi;
                             hi.x = pack_bf16x2(g8[0], g8[1]); hi.y = pack_bf16x2(g8[2], g8[3]);
@@ -590,29 +592,33 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (valid) {
                     const size_t o = obase + c * 32;
                     if (p.out_f32) {
-                        float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int q = 0; q < 4; ++q)       // 128 contiguous bytes per lane: four full-sector stores
+                            st_global_256(p.out_f32 + o + 8 * q,
+                                          make_uint4(__float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]),
+                                                     __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3])),
+                                          make_uint4(__float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]),
+                                                     __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7])));
                     } else {
-                        uint4* d = reinterpret_cast<uint4*>(p.out_hi + o);
+                        uint4 hi[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            uint4 hi;
-                            hi.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]); hi.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-                            hi.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); hi.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-                            d[q] = hi;
+                            hi[q].x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]); hi[q].y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                            hi[q].z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); hi[q].w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
                         }
+                        st_global_256(p.out_hi + o, hi[0], hi[1]);          // 64 contiguous bytes per lane: two full sectors
+                        st_global_256(p.out_hi + o + 16, hi[2], hi[3]);
                         if (p.out_lo) {
-                            uint4* e = reinterpret_cast<uint4*>(p.out_lo + o);
+                            uint4 lo[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                uint4 lo;
-                                lo.x = pack_bf16x2(v[8 * q + 0] - bf16_round(v[8 * q + 0]), v[8 * q + 1] - bf16_round(v[8 * q + 1]));
-                                lo.y = pack_bf16x2(v[8 * q + 2] - bf16_round(v[8 * q + 2]), v[8 * q + 3] - bf16_round(v[8 * q + 3]));
-                                lo.z = pack_bf16x2(v[8 * q + 4] - bf16_round(v[8 * q + 4]), v[8 * q + 5] - bf16_round(v[8 * q + 5]));
-                                lo.w = pack_bf16x2(v[8 * q + 6] - bf16_round(v[8 * q + 6]), v[8 * q + 7] - bf16_round(v[8 * q + 7]));
-                                e[q] = lo;
+                                lo[q].x = pack_bf16x2(v[8 * q + 0] - bf16_round(v[8 * q + 0]), v[8 * q + 1] - bf16_round(v[8 * q + 1]));
+                                lo[q].y = pack_bf16x2(v[8 * q + 2] - bf16_round(v[8 * q + 2]), v[8 * q + 3] - bf16_round(v[8 * q + 3]));
+                                lo[q].z = pack_bf16x2(v[8 * q + 4] - bf16_round(v[8 * q + 4]), v[8 * q + 5] - bf16_round(v[8 * q + 5]));
+                                lo[q].w = pack_bf16x2(v[8 * q + 6] - bf16_round(v[8 * q + 6]), v[8 * q + 7] - bf16_round(v[8 * q + 7]));
                             }
+                            st_global_256(p.out_lo + o, lo[0], lo[1]);
+                            st_global_256(p.out_lo + o + 16, lo[2], lo[3]);
                         }
                     }
                 }

@@ -252,6 +252,14 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
+// one 32-byte global store (sm_100 has 256-bit LSU accesses): a lane that owns 16 consecutive bf16 channels writes a
+// whole 32-byte sector in one instruction instead of two half-sector ones.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
