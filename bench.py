@@ -296,7 +296,7 @@ def run_b200(args):
                 "kernel": "fadb_vggish_front_conv1_tc_kernel (fp64 FFT log-mel front end fused with tcgen05 conv1)",
                 "ms_per_step": front_ms, "step_share": front_ms / ms_step if ms_step > 0 else None,
                 "actual_bytes_per_clip": 640000 + 10 * 48 * 32 * 64 * 2,
-                "note": "bound by shared-memory wavefronts of the fp64 FFT and TMEM reads of conv1, not by HBM"}
+                "note": "not HBM bound: a latency / shared-memory limited fp64 FFT phase plus the drain of the conv1 accumulators"}
 
     # ---- e2e through the public API from pinned host memory
     bg_h = torch.empty(bg.shape, dtype=torch.float32).pin_memory()
