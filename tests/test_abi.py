@@ -46,6 +46,8 @@ def test_library_is_sm100a_tcgen05_tma():
     assert "sm_100a" in sass
     for mnem in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnem in sass, mnem
+    assert "UTCHMMA.2CTA" in sass                      # the CTA-pair variant (cta_group::2) is built in
+    assert "STG.E.ENL2.256" in sass                    # 32-byte epilogue stores
 
 
 def test_frontend_rows_matches_oracle(lib):
