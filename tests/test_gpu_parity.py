@@ -412,3 +412,20 @@ def test_device_resampler_equals_host_restatement(eng_vgg, sr_in, sr_out, n):
     wide = torch.zeros((3, n + 5), dtype=torch.float32, device="cuda")
     wide[:, :n] = torch.from_numpy(clips).cuda()
     assert np.array_equal(eng_vgg.resample(wide[:, :n], sr_in, sr_out).cpu().numpy(), ref)
+
+
+def test_fad_properties_at_bench_scale(vgg_sd):
+    """BASELINE configs[3]-style sets (ten-second clips, thousands of patches, several network batches): properties that
+    do not need the CPU oracle — FAD is symmetric in its arguments, invariant to the order of the clips, zero for a set
+    against itself, and the host-streamed path equals the device-resident one."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = (torch.randn((1800, 160000), device="cuda", generator=g) * 0.1).clamp_(-1, 1)      # 18 000 patches: 2 batches
+    b = (torch.randn((900, 160000), device="cuda", generator=g) * 0.25).clamp_(-1, 1)
+    fab, fba = fad.score_clips(a, b), fad.score_clips(b, a)
+    assert np.isfinite(fab) and fab > 0 and abs(fab - fba) <= 1e-9 * fab
+    perm = torch.randperm(a.shape[0], generator=torch.Generator().manual_seed(0)).cuda()
+    assert abs(fad.score_clips(a[perm], b) - fab) <= 1e-9 * fab                          # fp64 sums: order-independent to rounding
+    assert abs(fad.score_clips(a, a)) <= 1e-9 * fab
+    assert abs(fad.score_clips(a[:600].cpu(), b[:300].cpu()) - fad.score_clips(a[:600], b[:300])) <= 1e-12 * fab
