@@ -12,7 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FADB_LIB_PATH") or os.path.join(_HERE, "libfadb200.so")   # override: A/B profiling only
 
 MODEL_IDS = {"vggish": 0, "pann-8k": 1, "pann-16k": 2, "pann-32k": 3, "clap": 4}
-PREC_IDS = {"bf16": 0, "bf16x3": 1}
+# arithmetic of the tensor-core layers (include/fadb.h FADB_PREC_*); "fp16x2" is the library default
+PREC_IDS = {"bf16": 0, "bf16x3": 1, "fp16": 2, "fp16x2": 3}
+# what fadb_weights_commit packs for a precision: (16-bit format, lo plane present)
+PREC_PACKING = {"bf16": ("bf16", False), "bf16x3": ("bf16", True), "fp16": ("fp16", False), "fp16x2": ("fp16", True)}
 
 # every symbol include/fadb.h declares: (name, restype, argtypes)
 _vp, _i64, _i32, _fp, _dp = C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p

@@ -43,21 +43,40 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _compile_one(args):
+    nvcc, src, obj, verbose = args
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    return src, r.returncode, r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu to an object (in parallel, one nvcc per source) and link libfadb200.so.  Objects go to the
+    git-ignored build/ directory at the repo root; the .so stays next to the package so it travels with the tree."""
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
                 return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    objdir = os.path.join(os.path.dirname(HERE), "build")
+    os.makedirs(objdir, exist_ok=True)
     print("[fadb] building", LIB, flush=True)
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    jobs = [(nvcc, os.path.join(CSRC, s), os.path.join(objdir, s.replace(".cu", ".o")), verbose) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(_compile_one, jobs))
+    failed = [r for r in results if r[1] != 0]
+    for src, rc, out in results:
+        if rc != 0 or verbose:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc failed building libfadb200.so: " + ", ".join(os.path.basename(r[0]) for r in failed))
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"] +
+                       [j[2] for j in jobs] + ["-o", LIB], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libfadb200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("linking libfadb200.so failed")
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB

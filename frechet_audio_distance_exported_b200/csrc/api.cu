@@ -43,7 +43,7 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
 // x [B, Ht, Wf, C] bf16 (hi + optional lo) -> mean over Wf, then max over Ht + mean over Ht  (pann.py:263-268)
 __global__ void cnn14_global_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                          int Ht, int Wf, int C, __nv_bfloat16* __restrict__ ohi,
-                                         __nv_bfloat16* __restrict__ olo) {
+                                         __nv_bfloat16* __restrict__ olo, int f16) {
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -53,7 +53,7 @@ __global__ void cnn14_global_pool_kernel(const __nv_bfloat16* __restrict__ hi, c
         float m = 0.f;
         for (int f = 0; f < Wf; ++f) {
             const size_t o = base + ((size_t)t * Wf + f) * C;
-            float v = __bfloat162float(hi[o]);
+            float v = f16 ? __half2float(reinterpret_cast<const __half*>(hi)[o]) : __bfloat162float(hi[o]);
             if (lo) v += __bfloat162float(lo[o]);
             m += v;
         }
@@ -62,6 +62,10 @@ __global__ void cnn14_global_pool_kernel(const __nv_bfloat16* __restrict__ hi, c
         sum += m;
     }
     const float r = mx + sum / (float)Ht;
+    if (f16) {
+        reinterpret_cast<__half*>(ohi)[(size_t)b * C + c] = __float2half_rn(fminf(r, 65504.f));
+        return;
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(r);
     ohi[(size_t)b * C + c] = h;
     if (olo) olo[(size_t)b * C + c] = __float2bfloat16_rn(r - __bfloat162float(h));
@@ -89,7 +93,8 @@ int launch_cnn14_global_pool(fadb_handle* h, const __nv_bfloat16* x_hi, const __
                              int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
     dim3 grid((C + 255) / 256, (unsigned)B);
     const bool x3 = h->precision == FADB_PREC_BF16X3;
-    cnn14_global_pool_kernel<<<grid, 256, 0, st>>>(x_hi, x3 ? x_lo : nullptr, Ht, Wf, C, out_hi, x3 ? out_lo : nullptr);
+    cnn14_global_pool_kernel<<<grid, 256, 0, st>>>(x_hi, x3 ? x_lo : nullptr, Ht, Wf, C, out_hi, x3 ? out_lo : nullptr,
+                                                   (int)prec_is_f16(h->precision));
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
@@ -154,10 +159,13 @@ static int add_layer(fadb_handle* h, const float* w, int Cout, int Cin, int ksiz
     L.taps = ksize * ksize;
     L.K = L.taps * Cin;
     const size_t n = (size_t)L.N * L.K;
+    // 16-bit planes in the format of the handle's precision; the lo plane (w - hi) only for the split-weight modes
+    L.f16 = prec_is_f16(h->precision) ? 1 : 0;
+    const bool want_lo = h->precision == FADB_PREC_BF16X3 || h->precision == FADB_PREC_FP16X2;
     FADB_CUDA_CHECK(cudaMalloc(&L.w_hi, n * sizeof(__nv_bfloat16)));
-    FADB_CUDA_CHECK(cudaMalloc(&L.w_lo, n * sizeof(__nv_bfloat16)));
+    if (want_lo) FADB_CUDA_CHECK(cudaMalloc(&L.w_lo, n * sizeof(__nv_bfloat16)));
     FADB_CUDA_CHECK(cudaMalloc(&L.bias, (size_t)Cout * sizeof(float)));
-    FADB_CHECK(pack_conv_weight(h, w, Cout, Cin, ksize, scale, L.w_hi, L.w_lo, st));
+    FADB_CHECK(pack_conv_weight(h, w, Cout, Cin, ksize, scale, L.w_hi, L.w_lo, L.f16 != 0, st));
     if (bias_or_shift)
         FADB_CUDA_CHECK(cudaMemcpyAsync(L.bias, bias_or_shift, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
     else
@@ -273,9 +281,11 @@ constexpr size_t kVggishActElems = 98304;        // max activation elements per 
 // tensor-core part of VGGishCore: a1 = conv1 output [P,48,32,64] (hi/lo) -> emb [P,128]
 static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __nv_bfloat16* a1_lo, int64_t P,
                             float* emb, cudaStream_t st) {
-    const size_t plane = (size_t)h->max_batch * kVggishActElems;            // largest later activation: 24*16*256
-    FADB_CHECK(h->ws_act[0].reserve(plane * 2 * sizeof(__nv_bfloat16)));
-    FADB_CHECK(h->ws_act[1].reserve(plane * 2 * sizeof(__nv_bfloat16)));
+    // sized for THIS batch (the buffers only ever grow); the lo plane exists in the bf16x3 mode only
+    const size_t plane = (size_t)P * kVggishActElems;                       // largest later activation: 24*16*256
+    const size_t nplanes = h->precision == FADB_PREC_BF16X3 ? 2 : 1;
+    FADB_CHECK(h->ws_act[0].reserve(plane * nplanes * sizeof(__nv_bfloat16)));
+    FADB_CHECK(h->ws_act[1].reserve(plane * nplanes * sizeof(__nv_bfloat16)));
     __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
     __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
     const int B = (int)P;
@@ -310,18 +320,19 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
     return FADB_OK;
 }
 
-static int reserve_a1(fadb_handle* h, int buf) {
-    return h->ws_a1[buf].reserve((size_t)h->max_batch * kVggishActElems * 2 * sizeof(__nv_bfloat16));
+static int reserve_a1(fadb_handle* h, int buf, int64_t P) {
+    const size_t nplanes = h->precision == FADB_PREC_BF16X3 ? 2 : 1;
+    return h->ws_a1[buf].reserve((size_t)P * kVggishActElems * nplanes * sizeof(__nv_bfloat16));
 }
-static inline __nv_bfloat16* a1_lo_plane(fadb_handle* h, int buf) {
-    return h->ws_a1[buf].as<__nv_bfloat16>() + (size_t)h->max_batch * kVggishActElems;
+static inline __nv_bfloat16* a1_lo_plane(fadb_handle* h, int buf, int64_t P) {
+    return h->ws_a1[buf].as<__nv_bfloat16>() + (size_t)P * kVggishActElems;
 }
 
 static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* emb, cudaStream_t st) {
-    FADB_CHECK(reserve_a1(h, 0));
+    FADB_CHECK(reserve_a1(h, 0, P));
     __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
-    FADB_CHECK(launch_conv1_vggish(h, feats, P, a1, a1_lo_plane(h, 0), st));           // [P,48,32,64]
-    return vggish_tc_layers(h, a1, a1_lo_plane(h, 0), P, emb, st);
+    FADB_CHECK(launch_conv1_vggish(h, feats, P, a1, a1_lo_plane(h, 0, P), st));        // [P,48,32,64]
+    return vggish_tc_layers(h, a1, a1_lo_plane(h, 0, P), P, emb, st);
 }
 
 // PCM -> embeddings for VGGish, chunked.  (A side stream running front end + conv1 of chunk i+1 under the tcgen05
@@ -337,13 +348,15 @@ static int vggish_embed_pcm(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t
         const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
         if (h->fused_front) {
             // front end + conv1 in one kernel: the fp32 features never touch HBM
-            FADB_CHECK(reserve_a1(h, 0));
+            // (chunks only shrink at the tail, so the lo-plane offset of the first chunk is the largest)
+            const int64_t Pc = nc * rows;
+            FADB_CHECK(reserve_a1(h, 0, Pc));
             __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
             FADB_CHECK(launch_vggish_front_conv1(h, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride, a1,
-                                                 a1_lo_plane(h, 0), st));
-            FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0), nc * rows, emb + c0 * rows * d, st));
+                                                 a1_lo_plane(h, 0, Pc), st));
+            FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0, Pc), Pc, emb + c0 * rows * d, st));
         } else {
-            FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 96 * 64 * sizeof(float)));
+            FADB_CHECK(h->ws_feats.reserve((size_t)(n_clips < cpc ? n_clips : cpc) * rows * 96 * 64 * sizeof(float)));
             FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride,
                                        h->ws_feats.as<float>(), st));
             FADB_CHECK(vggish_forward(h, h->ws_feats.as<float>(), nc * rows, emb + c0 * rows * d, st));
@@ -355,9 +368,10 @@ static int vggish_embed_pcm(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t
 static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T, float* emb, cudaStream_t st) {
     const int B = (int)B64;
     const size_t per_clip = (size_t)T * 64 * 64;
-    const size_t plane = (size_t)h->max_batch_cnn14 * per_clip;
-    FADB_CHECK(h->ws_act[0].reserve(plane * 2 * sizeof(__nv_bfloat16)));
-    FADB_CHECK(h->ws_act[1].reserve(plane * 2 * sizeof(__nv_bfloat16)));
+    const size_t plane = (size_t)B * per_clip;                                // this batch; the buffers only ever grow
+    const size_t nplanes = h->precision == FADB_PREC_BF16X3 ? 2 : 1;
+    FADB_CHECK(h->ws_act[0].reserve(plane * nplanes * sizeof(__nv_bfloat16)));
+    FADB_CHECK(h->ws_act[1].reserve(plane * nplanes * sizeof(__nv_bfloat16)));
     __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
     __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
     FADB_CHECK(launch_conv1_cnn14(h, feats, B, T, a[0], l[0], st));                     // [B,T,64,64]
@@ -410,7 +424,7 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
 
 static int check_device_flag(fadb_handle* h) {
     if (h->err_flag_host && *h->err_flag_host != 0) {
-        set_error("device-side failure flag = %d (1 = pipeline timeout, 2 = non-finite result)", *h->err_flag_host);
+        set_error("device-side failure flag = %d (1 = tensor-core pipeline timeout)", *h->err_flag_host);
         return FADB_E_DEVICE;
     }
     return FADB_OK;
@@ -466,6 +480,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
+    if (rc == FADB_OK) rc = frechet_init(h);
     if (rc != FADB_OK) { fadb_destroy(h); return rc; }
     *out = h;
     return FADB_OK;
@@ -476,6 +491,7 @@ void fadb_destroy(fadb_handle* h) {
     cudaSetDevice(h->device);
     free_layers(h);
     free_staged(h);
+    frontend_release(h);
     h->weight_pool.release();
     h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
@@ -491,7 +507,7 @@ void fadb_destroy(fadb_handle* h) {
 }
 
 int fadb_set_precision(fadb_handle* h, int prec) {
-    if (!h || (prec != FADB_PREC_BF16 && prec != FADB_PREC_BF16X3)) { set_error("bad precision"); return FADB_E_INVALID; }
+    if (!h || prec < FADB_PREC_BF16 || prec > FADB_PREC_FP16X2) { set_error("bad precision"); return FADB_E_INVALID; }
     h->precision = prec;
     return FADB_OK;
 }
@@ -499,7 +515,8 @@ int fadb_set_precision(fadb_handle* h, int prec) {
 int fadb_set_max_batch(fadb_handle* h, int max_items) {
     if (!h || max_items < 1 || max_items > 65535) { set_error("max_batch must be in [1, 65535]"); return FADB_E_INVALID; }
     h->max_batch = max_items;
-    h->max_batch_cnn14 = max_items > 1024 ? 1024 : max_items;
+    // CNN14 clips per batch: the call can lower it below its default (128 clips = 2.2 GB of activations), never raise it
+    h->max_batch_cnn14 = max_items < 128 ? max_items : 128;
     return FADB_OK;
 }
 
@@ -614,7 +631,7 @@ static int embed_pcm_any(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_
         FADB_CHECK(vggish_embed_pcm(h, pcm, n_clips, n_samples, pcm_stride, rows, emb_dev, st));
     } else {
         const int64_t cpc = h->max_batch_cnn14;
-        FADB_CHECK(h->ws_feats.reserve((size_t)cpc * rows * 64 * sizeof(float)));
+        FADB_CHECK(h->ws_feats.reserve((size_t)(n_clips < cpc ? n_clips : cpc) * rows * 64 * sizeof(float)));
         for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
             const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
             FADB_CHECK(launch_frontend(h, model, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride,
@@ -787,7 +804,8 @@ int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, i
     __nv_bfloat16 *xh = nullptr, *xl = nullptr;
     FADB_CUDA_CHECK(cudaMalloc(&xh, n_in * 2));
     FADB_CUDA_CHECK(cudaMalloc(&xl, n_in * 2));
-    int rc = split_f32_to_bf16(h, x, (int64_t)n_in, xh, xl, st);
+    const bool f16 = prec_is_f16(h->precision);
+    int rc = split_f32_to_bf16(h, x, (int64_t)n_in, xh, xl, f16, st);
     PackedLayer L;
     L.N = Cout; L.Cin = Cin; L.taps = ksize * ksize; L.K = L.taps * Cin;
     const size_t nw = (size_t)L.N * L.K;
@@ -795,7 +813,8 @@ int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, i
         set_error("cudaMalloc failed");
         rc = FADB_E_NOMEM;
     }
-    if (rc == FADB_OK) rc = pack_conv_weight(h, w_dev, Cout, Cin, ksize, nullptr, L.w_hi, L.w_lo, st);
+    L.f16 = f16 ? 1 : 0;
+    if (rc == FADB_OK) rc = pack_conv_weight(h, w_dev, Cout, Cin, ksize, nullptr, L.w_hi, L.w_lo, f16, st);
     L.bias = const_cast<float*>(bias_dev);
     if (rc == FADB_OK) {
         LayerIO io;

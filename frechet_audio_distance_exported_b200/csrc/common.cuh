@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -69,13 +70,29 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// A packed tensor-core layer: B operand [N][K] K-major bf16 (hi + lo planes) and fp32 bias.
+// 16-bit operand format of a precision mode: IEEE fp16 (FP16 / FP16X2) or bf16 (BF16 / BF16X3)
+inline bool prec_is_f16(int prec) { return prec == FADB_PREC_FP16 || prec == FADB_PREC_FP16X2; }
+
+// A packed tensor-core layer: B operand [N][K] K-major, 16-bit (hi + lo planes, bf16 or fp16) and fp32 bias.
 struct PackedLayer {
     int N = 0, K = 0;      // K = taps * Cin
     int Cin = 0, taps = 0;
+    int f16 = 0;           // planes hold IEEE fp16 instead of bf16
     __nv_bfloat16* w_hi = nullptr;
     __nv_bfloat16* w_lo = nullptr;
     float* bias = nullptr;   // [N] (folded BN shift or conv/linear bias)
+};
+
+// Front-end constant tables of one model (twiddles, window, sparse mel bands), on the handle's device (frontend.cu)
+struct FrontTables {
+    double2* tw = nullptr;     // [NF]  exp(-2 pi i k / NF)
+    double* win = nullptr;     // [WIN] periodic Hann
+    int* band_start = nullptr; // [64]
+    int* band_len = nullptr;   // [64]
+    float* band_wt = nullptr;  // [wt_rows][32] fp32: row (h2 ? wt_off1 : 0) + i, column lane = weight i of band lane + 32*h2
+    int wt_rows = 0, wt_off1 = 0;
+    int nfft = 0, win_len = 0, hop = 0;
+    bool ready = false;
 };
 
 struct HostTensor {
@@ -90,7 +107,7 @@ struct HostTensor {
 struct fadb_handle {
     int device = 0;
     int sm_count = 148;
-    int precision = FADB_PREC_BF16;
+    int precision = FADB_PREC_FP16X2;
     int max_batch = 16384;          // VGGish patches per internal batch (fewer, larger launches: ~5 us gap each)
     int max_batch_cnn14 = 128;      // CNN14 clips per internal batch
     int gemm_smem_budget = 231168;  // bytes of smem for resident weights + pipeline stages per GEMM CTA
@@ -117,6 +134,7 @@ struct fadb_handle {
     float* bn0_scale = nullptr;
     float* bn0_shift = nullptr;
     std::vector<fadb::PackedLayer> layers;             // tensor-core layers in execution order
+    fadb::FrontTables front_tables[5];                 // per model, built on first use ON THIS HANDLE'S DEVICE
     fadb::DevBuf weight_pool;                          // backing store of all packed weights
 
     // activation workspace
@@ -153,6 +171,7 @@ struct PcmSrc {
 int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int64_t n_samples,
                     int64_t pcm_stride, float* feats, cudaStream_t st);
 int frontend_init(fadb_handle* h);
+void frontend_release(fadb_handle* h);
 int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                               __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
 
@@ -185,9 +204,10 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
 int gemm_init(fadb_handle* h);
 
 // pack.cu — weight repacking, BN folding, fp32 -> bf16 hi/lo split
+// (the planes are 16-bit words: bf16, or IEEE fp16 when f16 is set)
 int pack_conv_weight(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
-                     __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, cudaStream_t st);
-int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                     __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, bool f16, cudaStream_t st);
+int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo, bool f16,
                       cudaStream_t st);
 int fold_bn(fadb_handle* h, const float* gamma, const float* beta, const float* mean, const float* var, int C,
             float* scale, float* shift, cudaStream_t st);
@@ -206,6 +226,7 @@ int launch_stats_finalize(fadb_handle* h, const double* acc, int d, const double
                           cudaStream_t st);
 
 // frechet.cu
+int frechet_init(fadb_handle* h);
 int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const double* mu2, const double* s2, int d,
                    double* out, cudaStream_t st);
 

@@ -22,7 +22,7 @@ constexpr int kC1Band = 8;                       // pooled rows per CTA
 __global__ void __launch_bounds__(256, 2) conv1_vggish_kernel(const float* __restrict__ feats, const float* __restrict__ w,
                                                               const float* __restrict__ bias,
                                                               __nv_bfloat16* __restrict__ out_hi,
-                                                              __nv_bfloat16* __restrict__ out_lo) {
+                                                              __nv_bfloat16* __restrict__ out_lo, int f16) {
     constexpr int H = 96, W = 64, HP = 48, WP = 32;
     constexpr int ROWS = 2 * kC1Band + 2;
     __shared__ __align__(16) float s_in[ROWS][W + 4];      // pitch 68: rows stay 16-byte aligned
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256, 2) conv1_vggish_kernel(const float* __res
         in[r][2] = pack_f32x2(b.x, b.x); in[r][3] = pack_f32x2(b.y, b.y);
     }
     const size_t obase = ((size_t(patch) * HP + prow_base + lr) * WP + pc) * 64;
-    conv1_vggish_pixel(in, s_w, s_b, out_hi, out_lo, obase);
+    conv1_vggish_pixel(in, s_w, s_b, out_hi, out_lo, obase, f16);
 }
 
 // ---------------------------------------------------------------- CNN14: bn0 + conv + BN + ReLU
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __rest
                                                              const float* __restrict__ bn0_shift,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ out_hi,
-                                                             __nv_bfloat16* __restrict__ out_lo) {
+                                                             __nv_bfloat16* __restrict__ out_lo, int f16) {
     constexpr int W = 64;
     __shared__ float s_in[kC14Rows + 2][W + 2];
     __shared__ __align__(16) float s_w[9][64];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __rest
                     v[2 * j] = fmaxf(a0 + bb.x, 0.f);
                     v[2 * j + 1] = fmaxf(a1 + bb.y, 0.f);
                 }
-                store16(v, out_hi, out_lo, ((size_t(clip) * T + y) * W + x) * 64 + g * 16);
+                store16(v, out_hi, out_lo, ((size_t(clip) * T + y) * W + x) * 64 + g * 16, f16);
             }
         }
     }
@@ -144,7 +144,7 @@ int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, _
     FADB_REQUIRE(n_patches <= 65535, "conv1: at most 65535 patches per batch");
     dim3 grid(48 / kC1Band, (unsigned)n_patches);
     conv1_vggish_kernel<<<grid, 256, 0, st>>>(feats, h->conv1_w, h->conv1_b, out_hi,
-                                             h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);
+                                             h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr, (int)prec_is_f16(h->precision));
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
@@ -158,7 +158,7 @@ int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int 
     // kernel is bound by writing its 8.45 MB of bf16 activations per clip to HBM, so the CUDA-core version stays)
     dim3 grid((unsigned)((T + kC14Rows - 1) / kC14Rows), (unsigned)n_clips);
     conv1_cnn14_kernel<<<grid, 256, 0, st>>>(feats, T, h->bn0_scale, h->bn0_shift, h->conv1_w, h->conv1_b, out_hi,
-                                            h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr);
+                                            h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr, (int)prec_is_f16(h->precision));
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;

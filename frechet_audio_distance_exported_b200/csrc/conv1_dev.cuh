@@ -1,6 +1,7 @@
 // conv1_dev.cuh — device helpers shared by conv1.cu and the fused front-end + conv1 kernel (frontend.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace fadb {
@@ -10,6 +11,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bfr(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// activation pair in the handle's 16-bit format: bf16, or IEEE fp16 with saturation (FADB_PREC_FP16 / FP16X2)
+__device__ __forceinline__ uint32_t pack2a(float a, float b, int f16) {
+    if (f16) {
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
+    }
+    return pack2(a, b);
+}
 
 // Packed fp32x2 FMA (sm_100+): d.lo = a.lo*b.lo + c.lo, d.hi = a.hi*b.hi + c.hi in ONE issue slot.  A 3-register
 // scalar FFMA issues every other cycle per scheduler on Blackwell, so the packed form is what reaches the
@@ -35,10 +45,10 @@ __device__ __forceinline__ void st256(void* p, const uint4& a, const uint4& b) {
                  : "memory");
 }
 
-__device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi, __nv_bfloat16* lo, size_t o) {
+__device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi, __nv_bfloat16* lo, size_t o, int f16) {
     uint4 a, b;
-    a.x = pack2(v[0], v[1]); a.y = pack2(v[2], v[3]); a.z = pack2(v[4], v[5]); a.w = pack2(v[6], v[7]);
-    b.x = pack2(v[8], v[9]); b.y = pack2(v[10], v[11]); b.z = pack2(v[12], v[13]); b.w = pack2(v[14], v[15]);
+    a.x = pack2a(v[0], v[1], f16); a.y = pack2a(v[2], v[3], f16); a.z = pack2a(v[4], v[5], f16); a.w = pack2a(v[6], v[7], f16);
+    b.x = pack2a(v[8], v[9], f16); b.y = pack2a(v[10], v[11], f16); b.z = pack2a(v[12], v[13], f16); b.w = pack2a(v[14], v[15], f16);
     st256(hi + o, a, b);
     if (lo) {
         float r[16];
@@ -55,7 +65,7 @@ __device__ __forceinline__ void store16(const float (&v)[16], __nv_bfloat16* hi,
 // warp-uniform weight loads.  `in` = the 4x4 input window, every value duplicated into an f32x2 register.
 __device__ __forceinline__ void conv1_vggish_pixel(const unsigned long long (&in)[4][4], const float (*s_w)[64],
                                                    const float* s_b, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                                                   size_t obase) {
+                                                   size_t obase, int f16) {
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {               // 16 output channels per pass
         unsigned long long acc[4][8];           // 4 positions of the pooling window x 8 channel PAIRS
@@ -93,7 +103,7 @@ __device__ __forceinline__ void conv1_vggish_pixel(const unsigned long long (&in
             v[2 * j] = fmaxf(fmaxf(fmaxf(a0, b0), fmaxf(c0, d0)) + bb.x, 0.f);
             v[2 * j + 1] = fmaxf(fmaxf(fmaxf(a1, b1), fmaxf(c1, d1)) + bb.y, 0.f);
         }
-        store16(v, out_hi, out_lo, obase + g * 16);
+        store16(v, out_hi, out_lo, obase + g * 16, f16);
     }
 }
 

@@ -503,11 +503,23 @@ __global__ void frechet_combine_kernel(const double* __restrict__ mu1, const dou
         out[1] = scal[2];
         out[2] = scal[0];
         out[3] = dd;
-        if (!isfinite(fad) && err_flag) atomicExch(err_flag, DEVERR_NONFINITE);
+        // a non-finite result (NaN covariance from a one-row set, ...) is DATA, not a pipeline failure: it is returned
+        // in out[0] and the caller raises (fad.py's ValueError); the handle stays usable
+        (void)err_flag;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
+// per handle (= per device): kernel attributes are device state, a process may hold handles on several GPUs
+int frechet_init(fadb_handle* h) {
+    (void)h;
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(tridiag_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         3 * 8192 * (int)sizeof(double)));
+    FADB_CUDA_CHECK(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * 8192 * (int)sizeof(double)));
+    return FADB_OK;
+}
+
 int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const double* mu2, const double* s2, int d,
                    double* out, cudaStream_t st) {
     FADB_REQUIRE(d >= 1 && d <= 8192, "Frechet: d=%d out of range", d);
@@ -558,14 +570,6 @@ int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const do
     FADB_CUDA_CHECK(cudaMemsetAsync(vec0, 0, 2 * (2 * (size_t)d + 1) * sizeof(double), st));
     {
         const size_t smem = 3 * (size_t)d * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            FADB_CUDA_CHECK(cudaFuncSetAttribute(tridiag_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 3 * 8192 * (int)sizeof(double)));
-            FADB_CUDA_CHECK(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 2 * 8192 * (int)sizeof(double)));
-            attr_set = true;
-        }
         int grid = (d + 15) / 16;                        // 16 warps per CTA, one row per warp per sweep
         if (grid > h->sm_count) grid = h->sm_count;
         if (grid < 1) grid = 1;

@@ -25,17 +25,7 @@
 
 namespace fadb {
 
-struct FrontTables {
-    double2* tw = nullptr;     // [NF]  exp(-2 pi i k / NF)
-    double* win = nullptr;     // [WIN] periodic Hann
-    int* band_start = nullptr; // [64]
-    int* band_len = nullptr;   // [64]
-    float* band_wt = nullptr;  // [wt_rows][32] fp32: row (h2 ? wt_off1 : 0) + i, column lane = weight i of band lane + 32*h2
-    int wt_rows = 0, wt_off1 = 0;
-    int nfft = 0, win_len = 0, hop = 0;
-    bool ready = false;
-};
-static FrontTables g_tables[5];   // per model; built per process (device-global, read-only)
+// FrontTables (common.cuh) live in the handle: one set per model, on the handle's own device
 
 struct FrontParams {
     const void* pcm;    // fp32 samples, or int16 when pcm_i16
@@ -441,7 +431,7 @@ struct FusedTcSmem {
 
 __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_tc_kernel(
     const FrontParams p, const float* __restrict__ conv_w, const float* __restrict__ conv_b, int patches_per_clip,
-    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int* err_flag, int dbg) {
+    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int f16, int* err_flag, int dbg) {
     constexpr int NF = 512, M = 256;
     using S = FrontSmem<NF>;
     using F = FusedTcSmem;
@@ -582,10 +572,10 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                         g[j] = fmaxf(m + s_bias[half * 32 + sub * 16 + j], 0.f);
                     }
                     uint4 h0, h1;
-                    h0.x = pack_bf16x2(g[0], g[1]); h0.y = pack_bf16x2(g[2], g[3]);
-                    h0.z = pack_bf16x2(g[4], g[5]); h0.w = pack_bf16x2(g[6], g[7]);
-                    h1.x = pack_bf16x2(g[8], g[9]); h1.y = pack_bf16x2(g[10], g[11]);
-                    h1.z = pack_bf16x2(g[12], g[13]); h1.w = pack_bf16x2(g[14], g[15]);
+                    h0.x = pack_act2(g[0], g[1], f16); h0.y = pack_act2(g[2], g[3], f16);
+                    h0.z = pack_act2(g[4], g[5], f16); h0.w = pack_act2(g[6], g[7], f16);
+                    h1.x = pack_act2(g[8], g[9], f16); h1.y = pack_act2(g[10], g[11], f16);
+                    h1.z = pack_act2(g[12], g[13], f16); h1.w = pack_act2(g[14], g[15], f16);
                     st_global_256(out_hi + obase + sub * 16, h0, h1);
                     if (out_lo) {
 #pragma unroll
@@ -658,8 +648,8 @@ static void slaney_mel(int sr, int nfft, double fmin, double fmax, std::vector<s
     }
 }
 
-static int build_tables(int model) {
-    FrontTables& t = g_tables[model];
+static int build_tables(fadb_handle* h, int model) {
+    FrontTables& t = h->front_tables[model];
     if (t.ready) return FADB_OK;
     int sr = 16000;
     double fmin = 50, fmax = 8000;
@@ -728,6 +718,17 @@ int frontend_init(fadb_handle* h) {
     return FADB_OK;
 }
 
+void frontend_release(fadb_handle* h) {
+    for (FrontTables& t : h->front_tables) {
+        if (t.tw) cudaFree(t.tw);
+        if (t.win) cudaFree(t.win);
+        if (t.band_start) cudaFree(t.band_start);
+        if (t.band_len) cudaFree(t.band_len);
+        if (t.band_wt) cudaFree(t.band_wt);
+        t = FrontTables();
+    }
+}
+
 static int64_t pann_pad(int64_t t) {        // fad.py:53-59
     int64_t k = (t + 24 + 31) / 32;
     int64_t v = 32 * k - 24;
@@ -772,8 +773,8 @@ struct FrontProfile {
 // PCM -> conv1 output [n_clips * patches, 48, 32, 64] bf16 (hi / optional lo) in one kernel (VGGish only)
 int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                               __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
-    FADB_CHECK(build_tables(FADB_MODEL_VGGISH));
-    const FrontTables& t = g_tables[FADB_MODEL_VGGISH];
+    FADB_CHECK(build_tables(h, FADB_MODEL_VGGISH));
+    const FrontTables& t = h->front_tables[FADB_MODEL_VGGISH];
     const int64_t patches = frontend_rows(FADB_MODEL_VGGISH, n_samples);
     if (n_clips <= 0 || patches <= 0) return FADB_OK;
     FADB_REQUIRE(n_clips <= 65535 && n_samples < (1LL << 30), "fused front end: clip count / length out of range");
@@ -795,7 +796,7 @@ int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64
     const int64_t total = patches * n_clips;
     const int64_t slots = 2LL * h->sm_count;
     fadb_vggish_front_conv1_tc_kernel<<<(unsigned)(total < slots ? total : slots), kFrontWarps * 32, FusedTcSmem::kTotal, st>>>(
-        p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo, h->err_flag, front_dbg);
+        p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo, (int)prec_is_f16(h->precision), h->err_flag, front_dbg);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
@@ -805,8 +806,8 @@ int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int6
                     int64_t pcm_stride, float* feats, cudaStream_t st) {
     FADB_REQUIRE(model >= 0 && model <= 4, "unknown model %d", model);
     FADB_REQUIRE(n_samples > 0 && n_samples < (1LL << 30), "n_samples out of range");
-    FADB_CHECK(build_tables(model));
-    const FrontTables& t = g_tables[model];
+    FADB_CHECK(build_tables(h, model));
+    const FrontTables& t = h->front_tables[model];
     if (n_clips <= 0) return FADB_OK;
     FrontParams p;
     p.pcm = pcm.ptr;
@@ -829,8 +830,9 @@ int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int6
         p.rows_out = (int)(patches * 96);
         p.frames_valid = p.rows_out;
     } else if (model == FADB_MODEL_CLAP) {
-        FADB_REQUIRE(n_samples <= 480000, "CLAP clips are at most 480000 samples (10 s), got %lld", (long long)n_samples);
-        p.logical_len = 480000;                       // fad.py:356-359 zero-pads the waveform first
+        // fad.py:356-359 zero-pads the waveform to 480000 first; a longer clip keeps its samples and only the first
+        // 1001 frames survive (_pad_to_clap_time truncates, fad.py:87-89)
+        p.logical_len = n_samples > 480000 ? (int)n_samples : 480000;
         p.rows_out = 1001;
         p.frames_valid = 1001;
     } else {

@@ -43,7 +43,7 @@ struct GemmParams {
     CUtensorMap tmA[2];   // activations hi, lo : dims (C, W, H, B)
     CUtensorMap tmB[2];   // weights hi, lo     : dims (Ktot, N)
     CUtensorMap tmH;      // halo mode: activations hi with box (64 ch, 10 px, 18 rows, 1 image)
-    CUtensorMap tmBh;     // cluster mode: weights hi with box (64, BN/2): each CTA of a pair loads half and multicasts it
+    CUtensorMap tmBh[2];  // cluster mode: weights hi, lo with box (64, BN/2): each CTA of a pair loads half (and multicasts it)
     int W, H, B;
     int BW, BH, BB;       // box; BW*BH*BB == 128
     int tiles_w, tiles_h, tiles_b, tiles_n;
@@ -54,7 +54,8 @@ struct GemmParams {
     int num_units;        // work units of the static schedule: tiles, or (M-tile group, N tile) in cluster mode
     int cin_blocks;       // Cin / 64
     int taps;             // 9 or 1
-    int npass;            // 1 (bf16) or 3 (bf16x3)
+    int npass;            // operand passes over K: 1 = A*B (bf16 / fp16); 2 = A*B_hi, A*B_lo (fp16x2: split weights);
+                          // 3 = A_hi*B_hi, A_lo*B_hi, A_hi*B_lo (bf16x3)
     int N;                // Cout
     int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
     int kb_begin, kb_end; // K-block range of this launch (whole K unless the exact-accumulation path splits it)
@@ -101,7 +102,9 @@ struct GemmCfg {
 // ------------------------------------------------------------------------------------------------
 // PAIR = the cta_group::2 variant (clusters of two only).  It is a separate instantiation because a kernel that contains
 // cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
-template <int BN, bool PAIR>
+// F16 = activations and weights are IEEE fp16 instead of bf16 (same kind::f16 MMA at the same rate; 8x smaller operand
+// rounding error, range +-65504 with saturation in the epilogue).
+template <int BN, bool PAIR, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     const int kStages = p.stages;
@@ -184,6 +187,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     };
 
     const int kb_per_pass = p.taps * p.cin_blocks;
+    // which activation / weight plane a pass multiplies: npass 1: (0,0); 2: (0,0),(0,1); 3: (0,0),(1,0),(0,1)
+    auto pass_a = [&](int pass) { return (p.npass == 3 && pass == 1) ? 1 : 0; };
+    auto pass_b = [&](int pass) { return (p.npass == 3) ? (pass == 2 ? 1 : 0) : (pass == 1 ? 1 : 0); };
+    // instruction descriptor: D = f32 (bit 4), A / B format bf16 = 1 or f16 = 0 (bits 7, 10), both K-major, N (bits 17..), M (bits 24..)
+    constexpr uint32_t kFmtBits = F16 ? 0u : ((1u << 7) | (1u << 10));
 
     // pair mode (halo path): every load completes on the LEADER's barrier, which expects the bytes of both CTAs; each CTA
     // loads its own activations and its half of the weight rows; the leader alone issues and commits for both
@@ -195,9 +203,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         if constexpr (PAIR) tma_load_4d_2sm(m, mapa_rank(bar, 0), dst, c0, c1, c2, c3);
         else tma_load_4d(m, bar, dst, c0, c1, c2, c3);
     };
-    auto load_wgt = [&](uint32_t bar, uint32_t dst, int k0, int n0) {
-        if constexpr (PAIR) tma_load_2d_2sm(&p.tmBh, mapa_rank(bar, 0), dst, k0, n0 + crank * (BN / 2));
-        else tma_load_2d(&p.tmB[0], bar, dst, k0, n0);
+    auto load_wgt = [&](uint32_t bar, uint32_t dst, int k0, int n0, int plane) {
+        if constexpr (PAIR) tma_load_2d_2sm(&p.tmBh[plane], mapa_rank(bar, 0), dst, k0, n0 + crank * (BN / 2));
+        else tma_load_2d(&p.tmB[plane], bar, dst, k0, n0);
     };
     auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
         if constexpr (PAIR) umma_bf16_2sm(d, da, db, idesc, acc);
@@ -217,8 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             if (p.resb && unit0 < p.num_units) {
                 if (elect_one()) {
                     expect(bar_bres, (uint32_t)res_bytes);
-                    for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg)
-                        load_wgt(bar_bres, base + (kbg - p.kb_begin) * kBTile, kbg * kBlockK, 0);
+                    for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg) {      // resident layout: [plane][tap][channel block]
+                        const int plane = kbg / kb_per_pass;
+                        load_wgt(bar_bres, base + (kbg - p.kb_begin) * kBTile, (kbg - plane * kb_per_pass) * kBlockK, 0, plane);
+                    }
                 }
                 __syncwarp();
             }
@@ -261,8 +271,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 const uint32_t b_off = kABytes + (p.cluster > 1 ? crank * (Cfg::kBBytes >> cshift) : 0);
                 const int b_row = n0 + (p.cluster > 1 ? crank * (BN >> cshift) : 0);
                 for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg) {
-                    const CUtensorMap* ta = &p.tmA[pass == 1 ? 1 : 0];
-                    const CUtensorMap* tb = &p.tmB[pass == 2 ? 1 : 0];
+                    const CUtensorMap* ta = &p.tmA[pass_a(pass)];
+                    const int bsel = pass_b(pass);
+                    const CUtensorMap* tb = &p.tmB[bsel];
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     if constexpr (PAIR) {
@@ -271,14 +282,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             const uint32_t lead_full = mapa_rank(bar_full + 8 * stage, 0);
                             if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)stage_pitch);
                             tma_load_4d_2sm(ta, lead_full, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                            tma_load_2d_2sm(&p.tmBh, lead_full, sa + kABytes, kb * kBlockK, n0 + crank * (BN / 2));
+                            tma_load_2d_2sm(&p.tmBh[bsel], lead_full, sa + kABytes, kb * kBlockK, n0 + crank * (BN / 2));
                         }
                     } else {
                       if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
                         tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
                         if (p.cluster > 1)      // my slice of the weight tile, into every CTA of the cluster
-                            tma_load_2d_multicast(&p.tmBh, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row, cmask);
+                            tma_load_2d_multicast(&p.tmBh[bsel], bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row, cmask);
                         else
                             tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row);
                       }
@@ -308,20 +319,22 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 unit_tile(unit, m, n0);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
-                        if (elect_one()) {
-                            expect(bar_bfull + 8 * bs, (uint32_t)kBTile);
-                            load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (tap * p.cin_blocks + cb) * kBlockK, n0);
+                        for (int plane = 0; plane < p.npass; ++plane) {       // fp16x2: the hi and the lo weight tile of this tap
+                            mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
+                            if (elect_one()) {
+                                expect(bar_bfull + 8 * bs, (uint32_t)kBTile);
+                                load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (tap * p.cin_blocks + cb) * kBlockK, n0, plane);
+                            }
+                            __syncwarp();
+                            if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                         }
-                        __syncwarp();
-                        if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1 && p.halo) {
         // ======================= MMA issuer, halo mode =======================
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+        constexpr uint32_t idesc = (1u << 4) | kFmtBits | (uint32_t(BN >> 3) << 17) |
                                    (uint32_t((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
         int stage = 0, bs = 0, it = 0;
         uint32_t phase = 0, bphase = 0;
@@ -345,16 +358,18 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 tc_fence_after();
                 const uint64_t da0 = make_halo_desc(stage_base + stage * kHaloBytes);
                 if (p.resb) {
-                    const uint64_t db0 = make_sw128_desc(base + cb * kBTile);
                     const uint32_t bstep = (uint32_t)(p.cin_blocks * kBTile) >> 4;   // next tap, same channel block
                     if (elect_one()) {
+                        for (int plane = 0; plane < p.npass; ++plane) {              // fp16x2: hi weights, then lo weights
+                            const uint64_t db0 = make_sw128_desc(base + (plane * kb_per_pass + cb) * kBTile);
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
-                            const uint64_t db = db0 + (uint64_t)(tap * bstep);
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
+                                const uint64_t db = db0 + (uint64_t)(tap * bstep);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k)
-                                mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k | plane) != 0 ? 1u : 0u);
+                            }
                         }
                         commit(bar_empty + 8 * stage);                 // halo tile free again
                     }
@@ -362,19 +377,21 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 } else {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
-                        tc_fence_after();
                         const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);
-                        const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
-                        if (elect_one()) {
+                        for (int plane = 0; plane < p.npass; ++plane) {
+                            mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
+                            tc_fence_after();
+                            const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k)
-                                mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
-                            commit(bar_bempty + 8 * bs);
-                            if (tap == 8) commit(bar_empty + 8 * stage);
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k | plane) != 0 ? 1u : 0u);
+                                commit(bar_bempty + 8 * bs);
+                                if (tap == 8 && plane == p.npass - 1) commit(bar_empty + 8 * stage);
+                            }
+                            __syncwarp();
+                            if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                         }
-                        __syncwarp();
-                        if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                     }
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -385,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     } else if (warp == 1 && PAIR) {
         // ======================= MMA issuer, pair mode: rank 0 issues M = 256 MMAs for both CTAs =======
         if constexpr (PAIR) if (crank == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+            constexpr uint32_t idesc = (1u << 4) | kFmtBits | (uint32_t(BN >> 3) << 17) |
                                        (uint32_t((2 * kTileM) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -418,8 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     } else if (warp == 1) {
         // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) =======
         {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+            constexpr uint32_t idesc = (1u << 4) | kFmtBits | (uint32_t(BN >> 3) << 17) |
                                        (uint32_t(kTileM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -574,10 +590,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                                                      __float_as_uint(g8[7])));
                         } else {
                             uint4 hi;
-                            hi.x = pack_bf16x2(g8[0], g8[1]); hi.y = pack_bf16x2(g8[2], g8[3]);
-                            hi.z = pack_bf16x2(g8[4], g8[5]); hi.w = pack_bf16x2(g8[6], g8[7]);
+                            hi.x = pack_act2<F16>(g8[0], g8[1]); hi.y = pack_act2<F16>(g8[2], g8[3]);
+                            hi.z = pack_act2<F16>(g8[4], g8[5]); hi.w = pack_act2<F16>(g8[6], g8[7]);
                             *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
-                            if (p.out_lo) {
+                            if (!F16 && p.out_lo) {
                                 uint4 lo;
                                 lo.x = pack_bf16x2(g8[0] - bf16_round(g8[0]), g8[1] - bf16_round(g8[1]));
                                 lo.y = pack_bf16x2(g8[2] - bf16_round(g8[2]), g8[3] - bf16_round(g8[3]));
@@ -603,12 +619,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         uint4 hi[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            hi[q].x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]); hi[q].y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-                            hi[q].z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); hi[q].w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+                            hi[q].x = pack_act2<F16>(v[8 * q + 0], v[8 * q + 1]); hi[q].y = pack_act2<F16>(v[8 * q + 2], v[8 * q + 3]);
+                            hi[q].z = pack_act2<F16>(v[8 * q + 4], v[8 * q + 5]); hi[q].w = pack_act2<F16>(v[8 * q + 6], v[8 * q + 7]);
                         }
                         st_global_256(p.out_hi + o, hi[0], hi[1]);          // 64 contiguous bytes per lane: two full sectors
                         st_global_256(p.out_hi + o + 16, hi[2], hi[3]);
-                        if (p.out_lo) {
+                        if (!F16 && p.out_lo) {
                             uint4 lo[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -721,27 +737,23 @@ int gemm_init(fadb_handle* h) {
         }
         g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<64>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<128>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<256>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<64>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<128>::kMaxSmemBytes));
-    FADB_CUDA_CHECK(cudaFuncSetAttribute(fadb_gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<256>::kMaxSmemBytes));
+    for (void (*k)(GemmParams) : {fadb_gemm_tc_kernel<64, false, false>, fadb_gemm_tc_kernel<128, false, false>,
+                                  fadb_gemm_tc_kernel<256, false, false>, fadb_gemm_tc_kernel<64, true, false>,
+                                  fadb_gemm_tc_kernel<128, true, false>, fadb_gemm_tc_kernel<256, true, false>,
+                                  fadb_gemm_tc_kernel<64, false, true>, fadb_gemm_tc_kernel<128, false, true>,
+                                  fadb_gemm_tc_kernel<256, false, true>, fadb_gemm_tc_kernel<64, true, true>,
+                                  fadb_gemm_tc_kernel<128, true, true>, fadb_gemm_tc_kernel<256, true, true>})
+        FADB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kMaxSmemBytes));
     return FADB_OK;
 }
 
-static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB) {
+static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB, bool f16) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                          const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -752,12 +764,13 @@ static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H,
     return FADB_OK;
 }
 
-static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN) {
+static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN, bool f16) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                          const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -773,7 +786,12 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     FADB_REQUIRE(io.Cin == L.Cin && io.taps == L.taps, "layer/IO mismatch (Cin %d vs %d, taps %d vs %d)", io.Cin,
                  L.Cin, io.taps, L.taps);
     FADB_REQUIRE(io.taps == 9 || io.taps == 1, "taps must be 1 or 9");
-    const int npass = (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3 : 1;
+    const bool f16 = prec_is_f16(h->precision);
+    FADB_REQUIRE(L.f16 == (int)f16, "layer weights were packed for %s but the handle's precision wants %s: commit the weights "
+                 "again after fadb_set_precision", L.f16 ? "fp16" : "bf16", f16 ? "fp16" : "bf16");
+    // operand passes over K (see GemmParams::npass)
+    const int npass = (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3
+                      : (h->precision == FADB_PREC_FP16X2 && L.w_lo) ? 2 : 1;
     const int BN = (L.N % 256 == 0) ? 256 : (L.N % 128 == 0 ? 128 : 64);
     FADB_REQUIRE(L.N % BN == 0 && L.N >= 64, "Cout=%d must be a multiple of 64", L.N);
     FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
@@ -783,7 +801,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     // the A operand.  Only used when H is large against the 16-row tile (few wasted rows).
     int halo = 0;
     int BW = 1, BH = 1, BB = 1;
-    if (h->halo && io.taps == 9 && npass == 1 && io.W % 8 == 0 && io.H >= 16 &&
+    if (h->halo && io.taps == 9 && npass <= 2 && io.W % 8 == 0 && io.H >= 16 &&
         double((io.H + 15) / 16 * 16) / io.H <= 1.13) {
         halo = 1;
         BW = 8; BH = 16; BB = 1;
@@ -820,18 +838,15 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB));
-    if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1));
+    FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16));
+    if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1, f16));
     else p.tmH = p.tmA[0];
     p.halo = halo;
-    FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN));
-    if (npass == 3) {
-        FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB));
-        FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN));
-    } else {
-        p.tmA[1] = p.tmA[0];
-        p.tmB[1] = p.tmB[0];
-    }
+    FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN, f16));
+    p.tmA[1] = p.tmA[0];
+    p.tmB[1] = p.tmB[0];
+    if (npass == 3) FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16));
+    if (npass >= 2) FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN, f16));
     p.W = io.W; p.H = io.H; p.B = io.B;
     p.BW = BW; p.BH = BH; p.BB = BB;
     p.tiles_w = (io.W + BW - 1) / BW;
@@ -915,19 +930,32 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         // gemm_cluster = 1: when every CTA pair gets work; 2 (tests): whenever the layer has two M tiles;
         // 3: only layers with many M tiles per CTA
         const bool pair_mode = h->gemm_twocta && cs == 2;
-        if (h->gemm_cluster && (!pp.halo || (pair_mode && h->gemm_pair_halo)) && pp.raw == 0 && npass == 1 && num_m >= 2 &&
+        if (h->gemm_cluster && (!pp.halo || (pair_mode && h->gemm_pair_halo)) && pp.raw == 0 && npass <= 2 && num_m >= 2 &&
             (h->gemm_cluster == 2 || (h->gemm_cluster == 1 && pair_units >= h->sm_count / cs) ||
              (h->gemm_cluster == 3 && num_m >= 2 * h->sm_count))) {
             pp.cluster = cs;
             pp.num_units = pair_units;
             if (pair_mode) { pp.twocta = 1; apply(pair); smem = pair.smem; }
             g = cs * (h->sm_count / cs);
-            if (encode_weight_map(&pp.tmBh, L.w_hi, L.K, L.N, BN / cs) != FADB_OK) { pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; }
+            if (encode_weight_map(&pp.tmBh[0], L.w_hi, L.K, L.N, BN / cs, f16) != FADB_OK ||
+                (npass == 2 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16) != FADB_OK)) {
+                pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; pp.twocta = 0; apply(plain); smem = plain.smem;
+            }
+            if (npass != 2) pp.tmBh[1] = pp.tmBh[0];
         }
-        void (*kern)(GemmParams) = (BN == 256) ? fadb_gemm_tc_kernel<256, false>
-                                   : (BN == 128 ? fadb_gemm_tc_kernel<128, false> : fadb_gemm_tc_kernel<64, false>);
-        void (*kern_pair)(GemmParams) = (BN == 256) ? fadb_gemm_tc_kernel<256, true>
-                                        : (BN == 128 ? fadb_gemm_tc_kernel<128, true> : fadb_gemm_tc_kernel<64, true>);
+        void (*kern)(GemmParams);
+        void (*kern_pair)(GemmParams);
+        if (f16) {
+            kern = (BN == 256) ? fadb_gemm_tc_kernel<256, false, true>
+                               : (BN == 128 ? fadb_gemm_tc_kernel<128, false, true> : fadb_gemm_tc_kernel<64, false, true>);
+            kern_pair = (BN == 256) ? fadb_gemm_tc_kernel<256, true, true>
+                                    : (BN == 128 ? fadb_gemm_tc_kernel<128, true, true> : fadb_gemm_tc_kernel<64, true, true>);
+        } else {
+            kern = (BN == 256) ? fadb_gemm_tc_kernel<256, false, false>
+                               : (BN == 128 ? fadb_gemm_tc_kernel<128, false, false> : fadb_gemm_tc_kernel<64, false, false>);
+            kern_pair = (BN == 256) ? fadb_gemm_tc_kernel<256, true, false>
+                                    : (BN == 128 ? fadb_gemm_tc_kernel<128, true, false> : fadb_gemm_tc_kernel<64, true, false>);
+        }
         void (*kern_plain)(GemmParams) = kern;
         if (pp.twocta) kern = kern_pair;
         cudaLaunchConfig_t cfg = {};
@@ -981,7 +1009,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         h->launches++;
     };
     const int nk = npass * io.taps * p.cin_blocks;
-    if (npass == 1) {
+    if (npass <= 2) {
         p.kb_begin = 0;
         p.kb_end = nk;
         p.raw = 0;

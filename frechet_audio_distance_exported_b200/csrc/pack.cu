@@ -4,10 +4,23 @@
 
 namespace fadb {
 
+// x -> {hi, lo} 16-bit words with x ~ hi + lo: bf16, or IEEE fp16 (lo may be an fp16 subnormal: absolute precision 6e-8)
+__device__ __forceinline__ void split16(float v, bool f16, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    if (f16) {
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        *reinterpret_cast<__half*>(hi) = h;
+        if (lo) *reinterpret_cast<__half*>(lo) = __float2half_rn(v - __half2float(h));
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        *hi = h;
+        if (lo) *lo = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 // [Cout][Cin][k][k] fp32  ->  [Cout][tap = ky*k+kx][Cin] bf16 hi (+lo), optionally scaled per Cout
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
                                         const float* __restrict__ scale, __nv_bfloat16* __restrict__ hi,
-                                        __nv_bfloat16* __restrict__ lo) {
+                                        __nv_bfloat16* __restrict__ lo, bool f16) {
     const size_t total = size_t(Cout) * Cin * kk;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int ci = int(i % Cin);
@@ -16,20 +29,14 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
         const int co = int(t / kk);
         float v = w[(size_t(co) * Cin + ci) * kk + tap];
         if (scale) v *= scale[co];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hi[i] = h;
-        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        split16(v, f16, hi + i, lo ? lo + i : nullptr);
     }
 }
 
 __global__ void split_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
-                             __nv_bfloat16* __restrict__ lo) {
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
-        const float v = x[i];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hi[i] = h;
-        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
-    }
+                             __nv_bfloat16* __restrict__ lo, bool f16) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        split16(x[i], f16, hi + i, lo ? lo + i : nullptr);
 }
 
 __global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, int C,
@@ -48,18 +55,18 @@ static inline int grid_for(size_t n) {
 }
 
 int pack_conv_weight(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
-                     __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, cudaStream_t st) {
+                     __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, bool f16, cudaStream_t st) {
     const size_t total = size_t(Cout) * Cin * ksize * ksize;
-    pack_conv_weight_kernel<<<grid_for(total), 256, 0, st>>>(w_oihw, Cout, Cin, ksize * ksize, scale, w_hi, w_lo);
+    pack_conv_weight_kernel<<<grid_for(total), 256, 0, st>>>(w_oihw, Cout, Cin, ksize * ksize, scale, w_hi, w_lo, f16);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
 }
 
-int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo, bool f16,
                       cudaStream_t st) {
     if (n <= 0) return FADB_OK;
-    split_kernel<<<grid_for((size_t)n), 256, 0, st>>>(x, (size_t)n, hi, lo);
+    split_kernel<<<grid_for((size_t)n), 256, 0, st>>>(x, (size_t)n, hi, lo, f16);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "common.cuh"
@@ -265,5 +266,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// fp16 activations (FADB_PREC_FP16 / FP16X2): 11 significand bits instead of 8; values beyond the fp16 range saturate
+// to +-65504 instead of becoming inf (one F2FP.SATFINITE instruction, like the bf16 pack)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_act2(float a, float b) {
+    if constexpr (F16) return pack_f16x2(a, b);
+    else return pack_bf16x2(a, b);
+}
+// run-time form for the kernels that are not templated on the activation format
+__device__ __forceinline__ uint32_t pack_act2(float a, float b, int f16) { return f16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
 
 }  // namespace fadb

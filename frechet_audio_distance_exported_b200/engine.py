@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MODEL_IDS, PREC_IDS, check
+from ._lib import MODEL_IDS, PREC_IDS, PREC_PACKING, check
 
 SAMPLE_RATES = {"vggish": 16000, "pann-8k": 8000, "pann-16k": 16000, "pann-32k": 32000, "clap": 48000}
 EMBED_DIMS = {"vggish": 128, "pann-8k": 2048, "pann-16k": 2048, "pann-32k": 2048, "clap": 512}
@@ -33,7 +33,7 @@ def _p(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, model_name: str, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 precision: str = "bf16", device: Optional[int] = None, max_batch: Optional[int] = None):
+                 precision: str = "fp16x2", device: Optional[int] = None, max_batch: Optional[int] = None):
         if model_name not in MODEL_IDS:
             raise ValueError(f"Unknown model: {model_name}. Valid options: {list(MODEL_IDS)}")
         _require_cuda()
@@ -46,12 +46,14 @@ class Engine:
         self.device = torch.device("cuda", self.device_index)
         self.handle = _lib.Handle(self.device_index)
         self.h = self.handle.ptr
+        self.weights_loaded = False
+        self._sd = None
+        self._packed = None
         self.set_precision(precision)
         self.max_batch = 16384                 # items per network launch (csrc/common.cuh default)
         if max_batch is not None:
             check(self.lib.fadb_set_max_batch(self.h, int(max_batch)))
             self.max_batch = int(max_batch)
-        self.weights_loaded = False
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -61,6 +63,11 @@ class Engine:
             raise ValueError(f"precision must be one of {list(PREC_IDS)}")
         check(self.lib.fadb_set_precision(self.h, PREC_IDS[precision]))
         self.precision = precision
+        # the packed weights are in the 16-bit format (bf16 / fp16, with or without the lo plane) of the precision
+        # they were committed under: re-pack when the new mode needs something else
+        fmt, lo = PREC_PACKING[precision]
+        if self.weights_loaded and (self._packed[0] != fmt or (lo and not self._packed[1])):
+            self.load_state_dict(self._sd)
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """Hand the reference modules' state_dict (VGGishCore / PANNCore key names) to the packer."""
@@ -73,6 +80,8 @@ class Engine:
             check(self.lib.fadb_weights_tensor(self.h, name.encode(), C.c_void_p(a.data_ptr()), shape, a.dim()))
         check(self.lib.fadb_weights_commit(self.h))
         self.weights_loaded = True
+        self._sd = sd
+        self._packed = PREC_PACKING[self.precision]
 
     # ------------------------------------------------------------------ hot path pieces (device tensors)
     def frontend_rows(self, n_samples: int) -> int:
@@ -222,6 +231,3 @@ class Engine:
                                              C.c_void_p(_stream_ptr())))
         return out
 
-
-def embeddings_to_numpy(t: torch.Tensor) -> np.ndarray:
-    return t.detach().to("cpu").numpy()

@@ -22,6 +22,7 @@ import torch
 
 from .engine import Engine
 from .resample import resample
+from .stream import HostRing
 
 CLAP_TIME_FRAMES = 1001                       # fad.py:38
 
@@ -70,6 +71,11 @@ def _pad_to_clap_time(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+class RawPCM16(np.ndarray):
+    """int16 samples straight from a 16-bit WAV file, still to be divided by 32768 (fad.py:148-149).  Only load_audio
+    creates it; a plain int16 ndarray handed to get_embeddings is NOT rescaled, like in the reference."""
+
+
 def load_audio(fname: str, sample_rate: int, channels: int, dtype: str = "float32", raw_pcm16: bool = False) -> np.ndarray:
     """fad.py:133-161 for RIFF/WAV files (PCM 8/16/24/32-bit and IEEE float), without libsndfile.
     raw_pcm16=True (not in the reference): a mono 16-bit file already at `sample_rate` is returned as the raw
@@ -79,7 +85,7 @@ def load_audio(fname: str, sample_rate: int, channels: int, dtype: str = "float3
 
     sr, raw = wavfile.read(fname)
     if raw_pcm16 and raw.dtype == np.int16 and raw.ndim == 1 and sr == sample_rate:
-        return raw
+        return raw.view(RawPCM16)
     if raw.dtype == np.uint8:
         f = (raw.astype(np.float64) - 128.0) / 128.0
     elif raw.dtype == np.int16:
@@ -134,7 +140,7 @@ class FrechetAudioDistance:
         audio_load_worker: int = 8,
         *,
         state_dict: Optional[Dict[str, torch.Tensor]] = None,
-        precision: str = "bf16",
+        precision: str = "fp16x2",
         process_group=None,
     ):
         if model_name not in VALID_MODELS:                                     # fad.py:205-208
@@ -203,8 +209,6 @@ class FrechetAudioDistance:
     # ------------------------------------------------------------------ fad.py:302-408
     def _check_length(self, n: int) -> None:
         """length limits at the model's own sample rate (after any resampling)"""
-        if self.model_name == "clap" and n > 480000:
-            raise ValueError("CLAP clips are limited to 10 s")
         if self.model_name != "vggish" and self.model_name != "clap":
             n_fft = {8000: 256, 16000: 512, 32000: 1024}[self.sample_rate]
             if n <= n_fft // 2:
@@ -213,9 +217,10 @@ class FrechetAudioDistance:
     def _prepare_clip(self, audio: np.ndarray, sr: int, device_resample: bool = False) -> np.ndarray:
         """Host part of vggish.py:241-250 / pann.py:93-101: mono mix, then resampling to the model's rate — on the
         host, or left to the GPU (`device_resample`: the clip comes back at its own rate, float32)."""
+        is_pcm16 = isinstance(audio, RawPCM16)
         audio = np.asarray(audio)
-        raw16 = audio.dtype == np.int16 and audio.ndim == 1 and sr == self.sample_rate
-        if audio.dtype == np.int16 and not raw16:                              # raw PCM16 that needs host-side work first
+        raw16 = is_pcm16 and audio.ndim == 1 and sr == self.sample_rate
+        if is_pcm16 and not raw16:                                             # raw PCM16 that needs host-side work first
             audio = audio / 32768.0                                            # fad.py:148-149
         if audio.ndim > 1:                                                     # vggish.py:245-246 / pann.py:96-97
             audio = np.mean(audio, axis=1)
@@ -259,10 +264,7 @@ class FrechetAudioDistance:
                     for i in idxs:
                         results[i] = np.zeros((0, self.engine.dim), dtype=np.float32)
                     continue
-                pcm = torch.from_numpy(np.stack([prepared[i] for i in idxs])).to(self.device, non_blocking=False)
-                if on_device:
-                    pcm = self.engine.resample(pcm, sr, self.sample_rate)
-                emb = self.engine.embed_pcm(pcm).cpu().numpy()
+                emb = self._embed_group([prepared[i] for i in idxs], rows, sr if on_device else None)
                 for j, i in enumerate(idxs):
                     results[i] = emb[j * rows:(j + 1) * rows]
             except Exception as e:
@@ -272,6 +274,54 @@ class FrechetAudioDistance:
         if not embd_lst:
             return np.array([])                                                # fad.py:405-406
         return np.concatenate(embd_lst, axis=0)                                # fad.py:408
+
+    def _embed_group(self, clips: List[np.ndarray], rows: int, resample_from: Optional[int]) -> np.ndarray:
+        """Equal-length clips -> [len(clips) * rows, d] embeddings, pipelined: the host gathers chunk i+1 into a pinned
+        staging buffer while chunk i is copied (copy stream) and chunk i-1 is embedded; the embeddings come back through
+        a pinned buffer with asynchronous copies and ONE synchronisation at the end (the reference does a blocking
+        round trip per clip, fad.py:389-396)."""
+        eng = self.engine
+        n, length, dtype = len(clips), clips[0].shape[0], torch.from_numpy(clips[0][:1]).dtype
+        chunk = max(1, min(n, self._chunk_clips(length)))
+        depth = 3
+        st = getattr(self, "_stage", None)
+        if st is None or st[0].shape != (chunk, length) or st[0].dtype != dtype:
+            st = self._stage = [torch.empty((chunk, length), dtype=dtype).pin_memory() for _ in range(depth)]
+            self._stage_ev = [torch.cuda.Event() for _ in range(depth)]
+            self._stage_used = [False] * depth
+        out_host = torch.empty((n * rows, eng.dim), dtype=torch.float32).pin_memory()
+        ring = self._ring()
+        cur = torch.cuda.current_stream()
+        slot = 0
+        for c0 in range(0, n, chunk):
+            nc = min(chunk, n - c0)
+            if self._stage_used[slot]:
+                self._stage_ev[slot].synchronize()                 # the copy that last read this pinned buffer is done
+            view = st[slot].numpy()
+            for j in range(nc):
+                view[j] = clips[c0 + j]
+
+            def consume(dev, _c0, _nc, c0=c0):
+                pcm = eng.resample(dev, resample_from, self.sample_rate) if resample_from else dev
+                emb = eng.embed_pcm(pcm)
+                out_host[c0 * rows:(c0 + _nc) * rows].copy_(emb, non_blocking=True)
+
+            ring.run(st[slot][:nc], nc, consume)
+            self._stage_ev[slot].record(ring.stream)
+            self._stage_used[slot] = True
+            slot = (slot + 1) % depth
+        cur.synchronize()
+        return out_host.numpy()
+
+    def _chunk_clips(self, n_samples: int) -> int:
+        """clips per host->device chunk: about 320 MB of fp32 PCM (512 ten-second 16 kHz clips were measured best on a
+        B200, 256 .. 1024 within 2 %)"""
+        return max(1, min(512, (320 << 20) // max(4 * n_samples, 1)))
+
+    def _ring(self) -> HostRing:
+        if getattr(self, "_host_ring", None) is None:
+            self._host_ring = HostRing(self.device, depth=4)
+        return self._host_ring
 
     def _get_embedding_for_audio(self, audio: np.ndarray) -> np.ndarray:
         """fad.py:410-481."""
@@ -363,9 +413,9 @@ class FrechetAudioDistance:
     # ------------------------------------------------------------------ B200 extensions
     def accumulate_clips(self, clips: torch.Tensor, acc: torch.Tensor, chunk_clips: Optional[int] = None) -> None:
         """Embed `clips` ([n, samples] fp32 or raw int16 PCM, HOST or device) and add their rows to the fp64 statistics
-        buffer `acc`.  Host tensors are streamed in chunks through two device buffers on a copy
-        stream so the host->device copy of chunk i+1 overlaps the kernels of chunk i (pin the host
-        tensor for this to be asynchronous).  Embeddings never leave the GPU."""
+        buffer `acc`.  Host tensors are streamed in chunks through a ring of four device buffers on a copy
+        stream, so the host->device copies run ahead of the kernels (pin the host tensor for this to be
+        asynchronous).  Embeddings never leave the GPU."""
         eng = self.engine
         n = clips.shape[0]
         if n == 0:
@@ -375,50 +425,29 @@ class FrechetAudioDistance:
             return
         assert clips.dtype in (torch.float32, torch.int16) and clips.dim() == 2 and clips.is_contiguous()
         if chunk_clips is None:
-            chunk_clips = 512          # measured on B200 (tools/prof_e2e.py): 256 .. 1024 are within 2 %, 384 - 512 best
+            chunk_clips = self._chunk_clips(clips.shape[1])
         chunk = min(chunk_clips, n)
-        cur = torch.cuda.current_stream()
-        if (getattr(self, "_h2d_bufs", None) is None or self._h2d_bufs[0].shape != (chunk, clips.shape[1])
-                or self._h2d_bufs[0].dtype != clips.dtype):
-            self._h2d_bufs = [torch.empty((chunk, clips.shape[1]), dtype=clips.dtype, device=self.device)
-                              for _ in range(2)]
-            self._h2d_stream = torch.cuda.Stream()
-            self._h2d_copied = [torch.cuda.Event(), torch.cuda.Event()]
-            self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-            self._h2d_next = 0
-            self._h2d_stream.wait_stream(cur)                  # fresh buffers: order after whatever ran before
-        # The copy stream only ever waits for the kernels that last READ the buffer it is about to overwrite
-        # (events persist across calls), so the first copy of a set overlaps the tail of the previous set; the
-        # first chunk of a call is half size, so the kernels start after half a chunk's copy time.
-        bounds, c0 = [], 0
-        first = max(1, chunk // 2) if n > chunk else chunk
-        while c0 < n:
-            nc = min(first if c0 == 0 else chunk, n - c0)
-            bounds.append((c0, nc))
-            c0 += nc
-        for c0, nc in bounds:
-            b = self._h2d_next
-            self._h2d_next ^= 1
-            with torch.cuda.stream(self._h2d_stream):
-                self._h2d_stream.wait_event(self._h2d_done[b])     # no-op until the event has been recorded once
-                self._h2d_bufs[b][:nc].copy_(clips[c0:c0 + nc], non_blocking=True)
-                self._h2d_copied[b].record(self._h2d_stream)
-            cur.wait_event(self._h2d_copied[b])
-            eng.stats_accumulate(eng.embed_pcm(self._h2d_bufs[b][:nc]), acc)
-            self._h2d_done[b].record(cur)
+        # ring of 4 device buffers on one copy stream (stream.HostRing): the copy engine runs up to four chunks ahead
+        # and only ever waits for the kernels that last READ the buffer it is about to overwrite; events persist across
+        # calls, so the first copy of a set overlaps the tail of the previous set.  The first chunk of a call is half
+        # size: the kernels start after half a chunk's copy time.
+        self._ring().run(clips, chunk, lambda dev, c0, nc: eng.stats_accumulate(eng.embed_pcm(dev), acc),
+                         first=max(1, chunk // 2))
 
-    def score_clips(self, background: torch.Tensor, evalset: torch.Tensor) -> float:
+    def score_clips(self, background: torch.Tensor, evalset: torch.Tensor, reduce: bool = True) -> float:
         """FAD of two in-memory clip sets ([n, samples] fp32 or raw int16 PCM, host or device).  With torch.distributed
         initialised each rank passes ITS shard (see dist.shard_bounds): it embeds the shard,
         accumulates {n, sum x, sum x x^T} in fp64, ONE all-reduce over `process_group`, then every
-        rank finalises mean/covariance and the Frechet distance redundantly."""
+        rank finalises mean/covariance and the Frechet distance redundantly.  reduce=False skips the all-reduce
+        (the rank scores what it was given, alone)."""
         eng = self.engine
         d = eng.dim
         both = torch.zeros(2 * (1 + d + d * d), dtype=torch.float64, device=self.device)
         half = both.numel() // 2
         self.accumulate_clips(background, both[:half])
         self.accumulate_clips(evalset, both[half:])
-        eng.allreduce_acc(both, self.process_group)
+        if reduce:
+            eng.allreduce_acc(both, self.process_group)
         mu1, s1 = eng.stats_finalize(both[:half], d)
         mu2, s2 = eng.stats_finalize(both[half:], d)
         return float(eng.frechet(mu1, s1, mu2, s2)[0].item())

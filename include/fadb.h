@@ -46,9 +46,14 @@ extern "C" {
 #define FADB_MODEL_PANN32K 3  /* "pann-32k" 32 kHz                           */
 #define FADB_MODEL_CLAP 4     /* "clap"     48 kHz CNN14 branch + head, 512-d L2-normalised */
 
-/* arithmetic of the tensor-core layers */
-#define FADB_PREC_BF16 0      /* bf16 operands, fp32 accumulate (north-star default) */
-#define FADB_PREC_BF16X3 1    /* split-bf16 (hi+lo) operands, 3 MMAs per product: ~fp32 accuracy */
+/* arithmetic of the tensor-core layers (all: tcgen05 kind::f16, fp32 accumulation in tensor memory) */
+#define FADB_PREC_BF16 0      /* bf16 activations x bf16 weights, 1 MMA per product: FAD within ~1e-4 .. 1e-3 of fp32 */
+#define FADB_PREC_BF16X3 1    /* split-bf16 (hi+lo) activations and weights, 3 MMAs per product + exact segment sums:
+                               * ~fp32 accuracy (embeddings 1e-5), slow; the strict parity mode */
+#define FADB_PREC_FP16 2      /* IEEE fp16 activations x fp16 weights, 1 MMA per product (same speed as BF16, 8x smaller
+                               * operand rounding; activations saturate at +-65504) */
+#define FADB_PREC_FP16X2 3    /* fp16 activations x split-fp16 (hi+lo) weights, 2 MMAs per product: the weights are exact to
+                               * ~2^-22, FAD within 1e-4 of the fp32 reference.  DEFAULT of a new handle. */
 
 typedef struct fadb_handle fadb_handle;
 
@@ -59,6 +64,8 @@ const char* fadb_last_error(void);
  * there is no CPU fallback. */
 int fadb_create(fadb_handle** out, int device);
 void fadb_destroy(fadb_handle* h);
+/* Packed weights are stored in the 16-bit format of the precision that was current at fadb_weights_commit (bf16 or
+ * fp16): after switching between the two families the weights must be committed again (FADB_E_STATE otherwise). */
 int fadb_set_precision(fadb_handle* h, int prec);
 /* max patches (VGGish) / clips (CNN14) per internal batch; sizes the activation workspace */
 int fadb_set_max_batch(fadb_handle* h, int max_items);

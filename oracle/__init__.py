@@ -5,7 +5,7 @@ This package restates, in NumPy / torch-CPU, the arithmetic of the reference
 embedding -> mean/cov -> Frechet distance).  Every function cites the reference
 file:line it follows.
 
-Rules (enforced by tests/test_no_oracle_in_product.py):
+Rules (enforced by tests/test_abi.py::test_product_never_imports_the_oracle):
   * only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
     `--impl reference` legs may import anything from here;
   * the product package `frechet_audio_distance_exported_b200` never imports it and has no

@@ -148,5 +148,77 @@ def main():
     print("golden fixtures written to", OUT)
 
 
+def main_configs():
+    """BASELINE.json configs as quoted (ten-second clips): the UNMODIFIED reference's get_embeddings / statistics /
+    Frechet on seeded clips.  Writes vggish_e2e_10s.npz, cnn14_10s.npz (separate from main() so the small fixtures
+    are not regenerated):
+
+        python -m oracle.make_golden --configs
+    """
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = ref_shim.load_reference()
+    from frechet_audio_distance_exported.models import vggish as rvgg, pann as rpann, clap as rclap
+    from frechet_audio_distance_exported import fad as rfad
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- VGGish, 48 + 48 ten-second clips (BASELINE configs[0] shape): FAD and statistics of the reference
+    sd = networks.vggish_random_state_dict(seed=0)
+    model = rvgg.VGGishCore()
+    model.load_state_dict(sd)
+    model.eval()
+    rf = ref_shim.make_reference_fad(ref, "vggish", model)
+    n, k = 160000, 48
+    bg = [synth.background_clip(i, n) for i in range(k)]
+    ev = [synth.eval_clip(i, n, 16000) for i in range(k)]
+    e_bg, e_ev = rf.get_embeddings(bg, 16000), rf.get_embeddings(ev, 16000)
+    mu1, s1 = rf.calculate_embd_statistics(e_bg)
+    mu2, s2 = rf.calculate_embd_statistics(e_ev)
+    fad_ref = float(rf.calculate_frechet_distance(mu1, s1, mu2, s2))
+    of = pipeline.OracleFAD("vggish", sd)
+    fad_o, o_bg, o_ev = of.fad_from_clips(bg[:4], ev[:4])
+    _check("vggish_e2e_10s/emb_bg[:4]", o_bg, e_bg[:40], 1e-5)
+    np.savez_compressed(os.path.join(OUT, "vggish_e2e_10s.npz"), n_samples=np.int64(n), n_clips=np.int64(k),
+                        emb_bg_head=e_bg[:40], emb_ev_head=e_ev[:40], mu1=mu1, sigma1=s1, mu2=mu2, sigma2=s2,
+                        fad=np.float64(fad_ref))
+    print(f"  vggish 10 s: {k}+{k} clips, FAD {fad_ref:.6f}")
+
+    # ---- CNN14 models, one ten-second clip each (T = 1001 -> 1032 / 1001) + PANN-16k 12 + 12 clips FAD
+    out = {}
+    sdp = networks.cnn14_random_state_dict(seed=1, clap_head=True)
+    pm = rpann.PANNCore()
+    pm.load_state_dict({k_: v for k_, v in sdp.items() if not k_.startswith("clap_head")})
+    pm.eval()
+    for name, sr in (("pann-8k", 8000), ("pann-16k", 16000), ("pann-32k", 32000)):
+        rfp = ref_shim.make_reference_fad(ref, name, pm)
+        c = synth.eval_clip(21, 10 * sr, sr)
+        e = rfp.get_embeddings([c], sr)                                       # fad.py:372-385 incl. the time padding
+        o = pipeline.OracleFAD(name, sdp).get_embeddings([c])
+        _check(f"cnn14_10s/{name}", o, e, 1e-5)
+        out[name.replace("-", "_")] = e
+    c = synth.eval_clip(22, 480000, 48000)
+    x = rfad._pad_to_clap_time(rclap.preprocess_for_clap(c, 48000, return_tensor=True))   # fad.py:356-362
+    with torch.no_grad():
+        h = pm(x)                                                             # the reference's PANNCore
+        h = torch.nn.functional.relu(torch.nn.functional.linear(h, sdp["clap_head.0.weight"], sdp["clap_head.0.bias"]))
+        h = torch.nn.functional.linear(h, sdp["clap_head.2.weight"], sdp["clap_head.2.bias"])
+        e = torch.nn.functional.normalize(h, dim=-1).numpy()                  # README.md:195-199 (no reference code)
+    _check("cnn14_10s/clap", pipeline.OracleFAD("clap", sdp).get_embeddings([c]), e, 1e-5)
+    out["clap"] = e
+    rfp = ref_shim.make_reference_fad(ref, "pann-16k", pm)
+    k = 12
+    bg = [synth.background_clip(100 + i, 160000) for i in range(k)]
+    ev = [synth.eval_clip(100 + i, 160000, 16000) for i in range(k)]
+    e_bg, e_ev = rfp.get_embeddings(bg, 16000), rfp.get_embeddings(ev, 16000)
+    mu1, s1 = rfp.calculate_embd_statistics(e_bg)
+    mu2, s2 = rfp.calculate_embd_statistics(e_ev)
+    fad_ref = float(rfp.calculate_frechet_distance(mu1, s1, mu2, s2))
+    out.update(pann16k_emb_bg=e_bg, pann16k_emb_ev=e_ev, pann16k_fad=np.float64(fad_ref), pann16k_clips=np.int64(k),
+               seed=np.int64(1))
+    np.savez_compressed(os.path.join(OUT, "cnn14_10s.npz"), **out)
+    print(f"  pann-16k 10 s: {k}+{k} clips, FAD {fad_ref:.6f}")
+    print("config fixtures written to", OUT)
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(main_configs() if "--configs" in sys.argv else main())

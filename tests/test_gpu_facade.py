@@ -107,7 +107,7 @@ def test_score_directories_and_cache(tmp_path, fad_vgg):
     ref, _, _ = ora.fad_from_clips([q(bg[i]) for i in order], [q(ev[i]) for i in
                                    [int(f[:3]) for f in os.listdir(str(tmp_path / "ev")) if not f.startswith(".")]])
     assert len(names) == 5
-    assert abs(s - ref) / abs(ref) < 5e-2                                  # bf16 mode, tiny rank-deficient sets
+    assert abs(s - ref) / abs(ref) < 2e-3                                  # default precision (fp16x2), tiny rank-deficient sets: 2x measured
     s16 = fad_vgg.score(str(tmp_path / "bg"), str(tmp_path / "ev"), dtype="int16")      # fad.py:145-149: raw PCM16 / 32768
     assert s16 == s                                                        # same samples, half the bytes over PCIe
     assert fad_vgg.score(str(tmp_path / "empty_missing"), str(tmp_path / "ev")) == -1     # exception -> -1, fad.py:660-662
@@ -149,8 +149,13 @@ def test_clap_facade():
     mu2, s2 = fad.calculate_embd_statistics(fad.get_embeddings(ev, 48000))
     f = fad.calculate_frechet_distance(mu1, s1, mu2, s2)
     assert np.isfinite(f) and f > 0
-    with pytest.raises(Exception):
-        fad._get_embedding_for_audio(np.zeros(480001, dtype=np.float32))   # > 10 s (tests/test_clap.py:133-140)
+    # > 10 s: get_embeddings does not raise (only the reference's pad_audio_to_max_length helper does,
+    # tests/test_clap.py:133-140); the log-mel is cut to 1001 frames, fad.py:87-89
+    long = np.concatenate([a, a, a, a, a, a[:4801]]).astype(np.float32)
+    assert long.shape[0] > 480000
+    el = fad._get_embedding_for_audio(long)
+    assert el.shape == (1, 512)
+    assert np.max(np.abs(el - pipeline.OracleFAD("clap", sd).embed_clip(long))) / np.max(np.abs(ref)) < 1e-4
 
 
 def test_encodec_is_out_of_scope():

@@ -3,8 +3,10 @@ through the C ABI (ctypes, via Engine / the façade), against the CPU oracle and
 vectors the UNMODIFIED reference produced (tests/golden/, oracle/make_golden.py).
 
 Tolerances (BASELINE.json north_star): log-mel 1e-5 relative (norm-wise: max|a-b| / max|b|),
-embeddings 1e-2 relative in bf16, FAD 1e-4 relative (bf16x3 "precise" mode end to end; exact
-statistics/Frechet kernels given identical embeddings in any mode).
+embeddings 1e-2 relative in bf16, FAD 1e-4 relative — met end to end by the default precision "fp16x2"
+(fp16 activations x split-fp16 weights) and by the strict mode "bf16x3"; the single-pass modes "bf16" / "fp16"
+are checked against 2x what was measured on a B200 (PRECISIONS below); the statistics / Frechet kernels are
+exact given identical embeddings in any mode.
 """
 import os
 
@@ -21,6 +23,14 @@ TOL_LOGMEL = 1e-5
 TOL_EMB_BF16 = 1e-2
 TOL_EMB_X3 = 1e-4          # measured 1.5e-5 (VGGish), 1.2e-5 (CNN14) with exact accumulation
 TOL_FAD = 1e-4
+# per precision mode: (embedding tolerance, end-to-end FAD tolerance on the 48 + 48 ten-second-clip golden set).
+# bf16x3 and fp16x2 carry the north-star bars; bf16 / fp16 are 2x the values measured on a B200.
+PRECISIONS = {
+    "bf16": (TOL_EMB_BF16, 4e-4),
+    "fp16": (2.5e-3, 2e-4),
+    "fp16x2": (2.5e-3, TOL_FAD),
+    "bf16x3": (TOL_EMB_X3, TOL_FAD),
+}
 # bf16x3 = split-bf16 operands + "exact accumulation" (K cut into 16-block segments summed in fp32 RN,
 # because the fp32 accumulator inside tcgen05.mma truncates: 5e-6 relative at K = 4608, linear in K).
 # Measured end-to-end FAD deviation in this mode: 8e-6 relative.
@@ -44,6 +54,24 @@ def eng_vgg(vgg_sd):
     return Engine("vggish", vgg_sd, precision="bf16")
 
 
+@pytest.fixture(scope="module")
+def eng_bare():
+    """handle without weights: single-layer tests switch precision freely (nothing to re-pack)"""
+    from frechet_audio_distance_exported_b200 import Engine
+    return Engine("vggish")
+
+
+def _rounded_operands(prec, x, w):
+    """what the kernel multiplies in each mode, as fp32 tensors (isolates the kernel from operand rounding)"""
+    if prec == "bf16":
+        return x.bfloat16().float(), w.bfloat16().float()
+    if prec == "fp16":
+        return x.half().float(), w.half().float()
+    if prec == "fp16x2":
+        return x.half().float(), w          # weights hi + lo: exact to 2^-22
+    return x, w
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core layer
 CONV_CASES = [
     # B, H, W, Cin, Cout, k, relu, pool
@@ -64,27 +92,24 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3", "fp16", "fp16x2"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_tcgen05_layer_matches_conv2d(eng_vgg, prec, case):
+def test_tcgen05_layer_matches_conv2d(eng_bare, prec, case):
     B, H, W, Cin, Cout, k, relu, pool = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
     x = torch.randn((B, H, W, Cin), generator=g)
     w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
     b = torch.randn(Cout, generator=g) * 0.1
-    eng_vgg.set_precision(prec)
-    try:
-        out = eng_vgg.debug_conv_layer(x.cuda(), w.cuda(), b.cuda(), k, bool(relu), pool).cpu().numpy()
-    finally:
-        eng_vgg.set_precision("bf16")
-    # bf16 mode: compare with fp64 conv of the bf16-ROUNDED operands (isolates the kernel from rounding)
-    xr, wr = (x.bfloat16().float(), w.bfloat16().float()) if prec == "bf16" else (x, w)
+    eng_bare.set_precision(prec)
+    out = eng_bare.debug_conv_layer(x.cuda(), w.cuda(), b.cuda(), k, bool(relu), pool).cpu().numpy()
+    # single-plane modes: compare with the fp64 conv of the ROUNDED operands (isolates the kernel from rounding)
+    xr, wr = _rounded_operands(prec, x, w)
     ref = F.conv2d(xr.permute(0, 3, 1, 2).double(), wr.double(), b.double(), padding=k // 2)
     ref = F.relu(ref) if relu else ref
     ref = F.max_pool2d(ref, 2) if pool == 1 else (F.avg_pool2d(ref, 2) if pool == 2 else ref)
     ref = ref.permute(0, 2, 3, 1).numpy()
     assert out.shape == ref.shape
-    assert relerr(out, ref) < (2e-5 if prec == "bf16" else 1e-4)
+    assert relerr(out, ref) < (1e-4 if prec == "bf16x3" else 2e-5)
 
 
 PAIR_MODES = {
@@ -94,18 +119,20 @@ PAIR_MODES = {
 }
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16x2"])
 @pytest.mark.parametrize("mode", sorted(PAIR_MODES))
-def test_cta_pair_modes_match_plain_launch(vgg_sd, monkeypatch, mode):
+def test_cta_pair_modes_match_plain_launch(vgg_sd, monkeypatch, mode, prec):
     """The cluster launches only trigger on layers with at least 74 work units, which none of the small cases above
     has; FADB_CLUSTER=2 forces them.  Every pair variant must reproduce the plain single-CTA kernel (same K order per
     output row), on every layer geometry incl. odd M-tile counts (the trailing tile of a pair runs on zero-filled
-    boxes), and through the whole VGGish network."""
+    boxes), and through the whole VGGish network — in the single-pass mode and in the two-pass split-weight mode
+    (hi and lo weight tiles through the pair's half-tile maps, the B ring and the resident-weight slab)."""
     from frechet_audio_distance_exported_b200 import Engine
     monkeypatch.setenv("FADB_CLUSTER", "0")
-    plain = Engine("vggish", vgg_sd, precision="bf16")
+    plain = Engine("vggish", vgg_sd, precision=prec)
     for k, v in PAIR_MODES[mode].items():
         monkeypatch.setenv(k, v)
-    paired = Engine("vggish", vgg_sd, precision="bf16")                  # the switches are read when the handle is created
+    paired = Engine("vggish", vgg_sd, precision=prec)                    # the switches are read when the handle is created
     for case in CONV_CASES:
         B, H, W, Cin, Cout, k, relu, pool = case
         g = torch.Generator().manual_seed(hash(case) % 1000)
@@ -169,9 +196,10 @@ def test_clap_frontend_golden(golden):
 
 
 # ------------------------------------------------------------------------------------------------ networks
-@pytest.mark.parametrize("prec,tol", [("bf16", TOL_EMB_BF16), ("bf16x3", TOL_EMB_X3)])
-def test_vggish_core_golden(vgg_sd, golden, prec, tol):
+@pytest.mark.parametrize("prec", sorted(PRECISIONS))
+def test_vggish_core_golden(vgg_sd, golden, prec):
     from frechet_audio_distance_exported_b200 import Engine
+    tol = PRECISIONS[prec][0]
     z = golden("vggish_core.npz")
     eng = Engine("vggish", vgg_sd, precision=prec)
     out = eng.embed_features(torch.from_numpy(z["patches"]).cuda()).cpu().numpy()
@@ -180,9 +208,10 @@ def test_vggish_core_golden(vgg_sd, golden, prec, tol):
     assert eng.launch_count() >= 9 and eng.device_status() == 0
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16", TOL_EMB_BF16), ("bf16x3", TOL_EMB_X3)])
-def test_cnn14_core_golden(golden, prec, tol):
+@pytest.mark.parametrize("prec", sorted(PRECISIONS))
+def test_cnn14_core_golden(golden, prec):
     from frechet_audio_distance_exported_b200 import Engine
+    tol = PRECISIONS[prec][0]
     z = golden("cnn14_core.npz")
     eng = Engine("pann-16k", networks.cnn14_random_state_dict(seed=int(z["seed"])), precision=prec)
     out = eng.embed_features(torch.from_numpy(z["feats"]).cuda()).cpu().numpy()
@@ -277,7 +306,10 @@ def test_vggish_fad_end_to_end_golden(vgg_sd, golden):
     n, k = int(z["n_samples"]), int(z["n_clips"])
     bg = [synth.background_clip(i, n) for i in range(k)]
     ev = [synth.eval_clip(i, n, 16000) for i in range(k)]
-    for prec, tol_e, tol_f in (("bf16", TOL_EMB_BF16, 5e-2), ("bf16x3", TOL_EMB_X3, TOL_FAD_E2E_X3)):
+    # 4 + 4 three-second clips = 12-row sets in 128-d: rank-deficient statistics amplify embedding noise, so the FAD
+    # bars here are looser than on the 48 + 48-clip set of test_vggish_fad_ten_second_golden (2x measured on a B200)
+    for prec, tol_e, tol_f in (("bf16", TOL_EMB_BF16, 4e-3), ("fp16", 2.5e-3, 1e-3), ("fp16x2", 2.5e-3, 5e-4),
+                               ("bf16x3", TOL_EMB_X3, TOL_FAD_E2E_X3)):
         fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd, precision=prec)
         eb, ee = fad.get_embeddings(bg, 16000), fad.get_embeddings(ev, 16000)
         assert eb.shape == z["emb_bg"].shape and eb.dtype == np.float32
@@ -388,10 +420,14 @@ def test_pcm16_host_paths(vgg_sd):
     s16 = fad.score_clips(torch.from_numpy(qb), torch.from_numpy(qe))
     s32 = fad.score_clips(torch.from_numpy(fb), torch.from_numpy(fe))
     assert s16 == s32 and abs(s16 - ref) / abs(ref) < 1e-9
-    # get_embeddings keeps mono native-rate int16 clips raw; mixed dtypes and lengths keep their order
-    out = fad.get_embeddings([qb[0], fb[1], qb[2][:16400]], 16000)
+    # get_embeddings keeps mono native-rate PCM16 clips from load_audio (RawPCM16) raw; mixed dtypes and lengths keep
+    # their order.  A PLAIN int16 ndarray is not rescaled — the reference does not either (vggish.py:241-250).
+    from frechet_audio_distance_exported_b200.fad import RawPCM16
+    out = fad.get_embeddings([qb[0].view(RawPCM16), fb[1], qb[2][:16400].view(RawPCM16)], 16000)
     assert out.shape == (2 + 2 + 1, 128)
     assert np.array_equal(out[:2], eb[:2]) and np.array_equal(out[2:4], eb[2:4])
+    plain = fad.get_embeddings([qb[0]], 16000)
+    assert np.array_equal(plain, fad.get_embeddings([qb[0].astype(np.float32)], 16000)) and not np.array_equal(plain, eb[:2])
 
 
 @pytest.mark.parametrize("sr_in,sr_out,n", [(44100, 16000, 44100), (8000, 16000, 12000), (48000, 32000, 50001),
@@ -429,3 +465,149 @@ def test_fad_properties_at_bench_scale(vgg_sd):
     assert abs(fad.score_clips(a[perm], b) - fab) <= 1e-9 * fab                          # fp64 sums: order-independent to rounding
     assert abs(fad.score_clips(a, a)) <= 1e-9 * fab
     assert abs(fad.score_clips(a[:600].cpu(), b[:300].cpu()) - fad.score_clips(a[:600], b[:300])) <= 1e-12 * fab
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs as quoted
+@pytest.mark.parametrize("prec", sorted(PRECISIONS))
+def test_vggish_fad_ten_second_golden(vgg_sd, golden, prec):
+    """BASELINE configs[0] shape: 48 + 48 ten-second clips, PCM -> FAD, against the UNMODIFIED reference's
+    get_embeddings + np.cov + scipy sqrtm (tests/golden/vggish_e2e_10s.npz, oracle/make_golden.py --configs).
+    The default precision (fp16x2) and the strict mode (bf16x3) meet the north-star 1e-4; bf16 / fp16 are held to
+    2x what a B200 measured."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    z = golden("vggish_e2e_10s.npz")
+    n, k = int(z["n_samples"]), int(z["n_clips"])
+    bg = torch.from_numpy(np.stack([synth.background_clip(i, n) for i in range(k)]))
+    ev = torch.from_numpy(np.stack([synth.eval_clip(i, n, 16000) for i in range(k)]))
+    fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd, precision=prec)
+    tol_e, tol_f = PRECISIONS[prec]
+    emb = fad.engine.embed_pcm(bg[:4].cuda()).cpu().numpy()
+    assert relerr(emb, z["emb_bg_head"]) < tol_e
+    f = fad.score_clips(bg, ev)
+    rel = abs(f - float(z["fad"])) / float(z["fad"])
+    print(f"[parity] vggish 48+48 ten-second clips, {prec}: FAD {f:.6f} vs reference {float(z['fad']):.6f} (rel {rel:.2e})")
+    assert rel < tol_f, (prec, rel)
+
+
+def test_default_precision_is_the_parity_mode(vgg_sd):
+    from frechet_audio_distance_exported_b200 import Engine, FrechetAudioDistance
+    assert FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd).engine.precision == "fp16x2"
+    assert Engine("vggish").precision == "fp16x2"
+
+
+@pytest.mark.parametrize("name,sr", [("pann-8k", 8000), ("pann-16k", 16000), ("pann-32k", 32000), ("clap", 48000)])
+def test_cnn14_ten_second_clip_golden(golden, name, sr):
+    """One ten-second clip per CNN14 model (T = 1001 -> 1032 frames, CLAP 1001): PCM -> front end -> bn0 -> 11 tensor-core
+    layers -> pooling -> FC (-> CLAP head) against the reference's get_embeddings (librosa shimmed, see ref_shim.py)."""
+    from frechet_audio_distance_exported_b200 import Engine
+    z = golden("cnn14_10s.npz")
+    sd = networks.cnn14_random_state_dict(seed=int(z["seed"]), clap_head=True)
+    ref = z[name.replace("-", "_")]
+    clip = synth.eval_clip(22 if name == "clap" else 21, 10 * sr, sr)
+    pcm = torch.from_numpy(clip)[None].cuda()
+    for prec, tol in (("bf16x3", TOL_EMB_X3), ("fp16x2", 2.5e-3), ("bf16", TOL_EMB_BF16)):
+        out = Engine(name, sd, precision=prec).embed_pcm(pcm).cpu().numpy()
+        assert out.shape == ref.shape
+        err = relerr(out, ref)
+        print(f"[parity] {name} ten-second clip, {prec}: embedding rel-max-err {err:.2e}")
+        assert err < tol, (name, prec, err)
+
+
+def test_pann16k_fad_ten_second_golden(golden):
+    """PANN-16k FAD (BASELINE configs[1] model) on 12 + 12 ten-second clips against the reference (2048-d, rank 11
+    covariances: the singular case of fad.py:538-544)."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    z = golden("cnn14_10s.npz")
+    sd = networks.cnn14_random_state_dict(seed=int(z["seed"]))
+    k = int(z["pann16k_clips"])
+    bg = torch.from_numpy(np.stack([synth.background_clip(100 + i, 160000) for i in range(k)]))
+    ev = torch.from_numpy(np.stack([synth.eval_clip(100 + i, 160000, 16000) for i in range(k)]))
+    for prec, tol_e, tol_f in (("bf16x3", TOL_EMB_X3, TOL_FAD), ("fp16x2", 2.5e-3, TOL_FAD), ("bf16", TOL_EMB_BF16, 5e-3)):
+        fad = FrechetAudioDistance(model_name="pann-16k", state_dict=sd, precision=prec)
+        eb = fad.get_embeddings(list(bg.numpy()), 16000)
+        assert eb.shape == (k, 2048) and relerr(eb, z["pann16k_emb_bg"]) < tol_e
+        f = fad.score_clips(bg, ev)
+        rel = abs(f - float(z["pann16k_fad"])) / float(z["pann16k_fad"])
+        print(f"[parity] pann-16k 12+12 ten-second clips, {prec}: FAD {f:.4f} (rel {rel:.2e})")
+        assert rel < tol_f, (prec, rel)
+
+
+@pytest.mark.parametrize("name,sr", [("pann-8k", 8000), ("pann-16k", 16000), ("pann-32k", 32000), ("clap", 48000)])
+def test_cnn14_frontend_vs_torch_second_opinion(name, sr):
+    """The PANN / CLAP front end's arithmetic lives in un-vendored librosa, so the golden vectors of this stage come
+    from the reference calling a stand-in.  This pins the CUDA kernel to an INDEPENDENT implementation instead:
+    torch.stft (centred, reflect, periodic Hann, fp64) + torchaudio's Slaney filterbank, at all four rates."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from frechet_audio_distance_exported_b200 import Engine
+    cfg = frontend.PANN_CONFIGS[sr]
+    x = synth.eval_clip(31, 2 * sr + 123, sr)
+    if name == "clap":
+        x = np.pad(x, (0, 480000 - x.shape[0]))                              # fad.py:356-359
+        x = frontend.clap_quantize(x)                                         # clap.py:70-72 (plain arithmetic)
+    st = torch.stft(torch.from_numpy(x).double(), cfg["n_fft"], cfg["hop"], cfg["n_fft"],
+                    window=torch.hann_window(cfg["n_fft"], periodic=True, dtype=torch.float64),
+                    center=True, pad_mode="reflect", return_complex=True)
+    power = (st.abs() ** 2).float()                                           # pann.py:118 (complex64 -> float32)
+    fb = torchaudio.functional.melscale_fbanks(cfg["n_fft"] // 2 + 1, cfg["fmin"], cfg["fmax"], 64, sr,
+                                               norm="slaney", mel_scale="slaney")
+    ref = (10.0 * torch.log10(torch.clamp(fb.T @ power, min=1e-10))).T.numpy()   # pann.py:130-139
+    out = Engine(name).frontend(torch.from_numpy(x)[None].cuda()).cpu().numpy()[0]
+    t = ref.shape[0] if name != "clap" else 1001
+    assert out.shape[0] >= t and np.all(out[t:] == 0.0)
+    # torchaudio builds the filterbank in float32 with its own rounding: 1e-4 dB-relative is the level the two CPU
+    # implementations agree to (tests/test_oracle.py); the kernel must sit inside the same band
+    assert relerr(out[:t], ref[:t]) < 1e-4
+
+
+def test_clap_long_clip_is_truncated_like_reference():
+    """fad.py:356-362: a clip longer than 10 s is not padded, its log-mel is cut to the first 1001 frames."""
+    from frechet_audio_distance_exported_b200 import Engine
+    x = synth.eval_clip(5, 480000 + 4800, 48000)
+    out = Engine("clap").frontend(torch.from_numpy(x)[None].cuda()).cpu().numpy()[0]
+    assert out.shape == (1001, 64)
+    assert relerr(out, frontend.clap_features(x)) < TOL_LOGMEL
+
+
+def test_nonfinite_frechet_does_not_poison_the_handle(vgg_sd):
+    """A one-row set has no covariance (np.cov -> NaN): the NaN comes back as data and the handle keeps working
+    (the reference object stays usable after the same input)."""
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    fad = FrechetAudioDistance(model_name="vggish", state_dict=vgg_sd)
+    eng = fad.engine
+    one = torch.from_numpy(synth.embedding_set(0, 1, 128)).cuda()
+    acc = eng.new_acc(128)
+    eng.stats_accumulate(one, acc)
+    mu, sg = eng.stats_finalize(acc, 128)
+    out = eng.frechet(mu, sg, mu, sg)
+    assert not np.isfinite(float(out[0])) and eng.device_status() == 0
+    with pytest.raises(ValueError):
+        fad.calculate_frechet_distance(mu.cpu().numpy(), sg.cpu().numpy(), mu.cpu().numpy(), sg.cpu().numpy())
+    clip = synth.eval_clip(0, 32400, 16000)
+    assert fad.get_embeddings([clip], 16000).shape == (2, 128)              # still alive
+
+
+def test_precision_switch_repacks_weights(vgg_sd):
+    """bf16 <-> fp16 families keep different packed weights: Engine.set_precision re-packs, and the result equals a
+    fresh engine of that precision (bit-exact)."""
+    from frechet_audio_distance_exported_b200 import Engine
+    feats = torch.randn(9, 96, 64, generator=torch.Generator().manual_seed(7)).cuda() * 2.0
+    eng = Engine("vggish", vgg_sd, precision="bf16")
+    ref = {}
+    for prec in ("fp16x2", "bf16", "fp16", "bf16x3", "fp16x2"):
+        eng.set_precision(prec)
+        out = eng.embed_features(feats).cpu().numpy()
+        if prec not in ref:
+            ref[prec] = Engine("vggish", vgg_sd, precision=prec).embed_features(feats).cpu().numpy()
+        assert np.array_equal(out, ref[prec]), prec
+    assert not np.array_equal(ref["bf16"], ref["fp16"])
+
+
+def test_two_handles_on_one_device_are_independent(vgg_sd):
+    """front-end tables and kernel attributes live in the handle (not in process globals)"""
+    from frechet_audio_distance_exported_b200 import Engine
+    a, b = Engine("vggish", vgg_sd), Engine("pann-16k")
+    clip = torch.from_numpy(synth.eval_clip(1, 32400, 16000))[None].cuda()
+    e1 = a.embed_pcm(clip).cpu().numpy()
+    f1 = b.frontend(clip).cpu().numpy()
+    del b
+    assert np.array_equal(a.embed_pcm(clip).cpu().numpy(), e1) and f1.shape == (1, 232, 64)

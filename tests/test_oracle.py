@@ -152,3 +152,29 @@ def test_oracle_skips_bad_clips_like_reference():
     assert of.get_embeddings([]).shape == (0,)                                     # fad.py:405-406
     out = of.get_embeddings([synth.sine_clip(0.5, 440.0, 16000), synth.sine_clip(1.0, 440.0, 16000)])
     assert out.shape == (1, 128)
+
+
+def test_config_size_goldens_match_oracle(golden):
+    """tests/golden/vggish_e2e_10s.npz, cnn14_10s.npz (oracle/make_golden.py --configs: the UNMODIFIED reference on
+    ten-second clips): the oracle restatement reproduces them (bounded: 2 VGGish clips, 1 PANN-16k clip, Frechet at d = 128)."""
+    z = golden("vggish_e2e_10s.npz")
+    sd = networks.vggish_random_state_dict(seed=0)
+    ora = pipeline.OracleFAD("vggish", sd)
+    n = int(z["n_samples"])
+    emb = ora.get_embeddings([synth.background_clip(i, n) for i in range(2)])
+    assert relerr(emb, z["emb_bg_head"][:20]) < 1e-5
+    fd = stats.frechet_distance(z["mu1"], z["sigma1"], z["mu2"], z["sigma2"])
+    assert abs(fd - float(z["fad"])) / float(z["fad"]) < 1e-9
+    c = golden("cnn14_10s.npz")
+    sdp = networks.cnn14_random_state_dict(seed=int(c["seed"]), clap_head=True)
+    e = pipeline.OracleFAD("pann-16k", sdp).get_embeddings([synth.eval_clip(21, 160000, 16000)])
+    assert e.shape == (1, 2048) and relerr(e, c["pann_16k"]) < 1e-5
+
+
+def test_host_ring_chunking():
+    from frechet_audio_distance_exported_b200.stream import chunk_bounds
+    assert chunk_bounds(10, 4) == [(0, 4), (4, 4), (8, 2)]
+    assert chunk_bounds(10, 4, first=2) == [(0, 2), (2, 4), (6, 4)]
+    assert chunk_bounds(0, 4) == [] and chunk_bounds(3, 8) == [(0, 3)]
+    b = chunk_bounds(12500, 512, first=256)
+    assert sum(n for _, n in b) == 12500 and all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
