@@ -340,9 +340,7 @@ static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* 
 static int vggish_embed_pcm(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
                             int64_t rows, float* emb, cudaStream_t st) {
     const int d = 128;
-    // the bf16x3 parity mode keeps raw fp32 partial sums of a whole layer: bound its batch to keep that scratch small
-    const int64_t batch = (h->precision == FADB_PREC_BF16X3 && h->max_batch > 4096) ? 4096 : h->max_batch;
-    int64_t cpc = batch / rows;                         // clips per chunk
+    int64_t cpc = h->max_batch / rows;                  // clips per chunk
     FADB_REQUIRE(cpc >= 1, "max_batch %d smaller than patches per clip %lld", h->max_batch, (long long)rows);
     for (int64_t c0 = 0; c0 < n_clips; c0 += cpc) {
         const int64_t nc = (n_clips - c0 < cpc) ? n_clips - c0 : cpc;
@@ -602,7 +600,7 @@ int fadb_embed(fadb_handle* h, const float* feats_dev, int64_t n_items, int64_t 
     const int d = embed_dim(h->model);
     if (h->model == FADB_MODEL_VGGISH) {
         if (t_frames != 96) { set_error("VGGish patches have 96 frames, got %lld", (long long)t_frames); return FADB_E_INVALID; }
-        const int64_t batch = (h->precision == FADB_PREC_BF16X3 && h->max_batch > 4096) ? 4096 : h->max_batch;
+        const int64_t batch = h->max_batch;
         for (int64_t i0 = 0; i0 < n_items; i0 += batch) {
             const int64_t n = (n_items - i0 < batch) ? n_items - i0 : batch;
             FADB_CHECK(vggish_forward(h, feats_dev + i0 * 96 * 64, n, emb_dev + i0 * d, st));

@@ -58,8 +58,13 @@ struct GemmParams {
                           // 3 = A_hi*B_hi, A_lo*B_hi, A_hi*B_lo (bf16x3)
     int N;                // Cout
     int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
-    int kb_begin, kb_end; // K-block range of this launch (whole K unless the exact-accumulation path splits it)
-    int raw;              // 0 = fused epilogue; 1 = write raw fp32 partial sums; 2 = add them to out_f32
+    int nkb;              // K blocks (of 64) per tile: npass * taps * cin_blocks
+    int nseg, seg_len;    // accumulation segments per tile and their length (K blocks; halo mode: channel blocks).
+                          // Each segment is its own accumulation chain in tensor memory (the two TMEM accumulators
+                          // alternate per SEGMENT); the epilogue warps add the segment sums in fp32 registers with
+                          // round-to-nearest.  The fp32 accumulation inside tcgen05.mma truncates, a bias that grows with
+                          // the chain length (5e-6 of the output at K = 4608) and shrinks every activation of every
+                          // layer the same way: cutting the chains to <= 64 MMAs removes it (FAD: 2e-4 -> 1e-5).
     int halo;             // 1 = halo mode: one activation tile per channel block feeds all 9 taps
     int b_stages;         // halo mode: depth of the separate B ring
     int resb;             // halo mode: 1 = all weights of the (single) N tile stay resident in smem
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     // layout: [resident B: nkb x kBBytes (resb only)] [stages] ([halo mode: B ring]) [barriers]
     constexpr int kBTile = PAIR ? Cfg::kBBytes / 2 : Cfg::kBBytes;   // bytes of one weight K block held by THIS CTA
-    const int res_bytes = p.resb ? (p.kb_end - p.kb_begin) * kBTile : 0;
+    const int res_bytes = p.resb ? p.nkb * kBTile : 0;
     const int stage_pitch = p.halo ? kHaloBytes : (PAIR ? kABytes + Cfg::kBBytes / 2 : Cfg::kStageBytes);
     const uint32_t stage_base = base + res_bytes;
     const uint32_t bring_base = stage_base + kStages * stage_pitch;           // halo mode only
@@ -171,6 +176,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     if (p.cluster > 1) cluster_sync_all();       // the peer's barriers exist before anything multicasts to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Register re-allocation per warpgroup: the control warps (TMA / MMA issue) need few registers, the epilogue warps
+    // hold BN/2 running fp32 sums per thread across the accumulation segments of a tile.  128 x 56 + 256 x 224 = 64512.
+    // (the setmaxnreg instructions open the two role branches below)
     // Static schedule.  Plain mode: unit = tile, N tile fastest.  Cluster mode: unit = (pair of M tiles, N tile); CTA
     // rank r of the pair takes M tile 2*pair + r, so both CTAs need the SAME weight tile at every K step and each
     // loads half of it, multicast to both.  An M tile past the end (odd count) runs on zero-filled boxes and stores
@@ -216,6 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         else umma_commit(bar);
     };
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ======================= TMA producer (whole warp runs the loop; one elected lane issues) =====
         if (p.halo) {
@@ -225,9 +235,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             if (p.resb && unit0 < p.num_units) {
                 if (elect_one()) {
                     expect(bar_bres, (uint32_t)res_bytes);
-                    for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg) {      // resident layout: [plane][tap][channel block]
+                    for (int kbg = 0; kbg < p.nkb; ++kbg) {                  // resident layout: [plane][tap][channel block]
                         const int plane = kbg / kb_per_pass;
-                        load_wgt(bar_bres, base + (kbg - p.kb_begin) * kBTile, (kbg - plane * kb_per_pass) * kBlockK, 0, plane);
+                        load_wgt(bar_bres, base + kbg * kBTile, (kbg - plane * kb_per_pass) * kBlockK, 0, plane);
                     }
                 }
                 __syncwarp();
@@ -262,15 +272,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 // K-block walk without integer divisions: this loop paces the whole pipeline (two runtime divisions
                 // per K block in it cost 9 % of the layer time when measured), so (pass, tap, channel block) and the
                 // tap offsets advance incrementally
-                int pass = p.kb_begin / kb_per_pass;
-                int kb = p.kb_begin - pass * kb_per_pass;
-                int tap = kb / p.cin_blocks;
-                int cb = kb - tap * p.cin_blocks;
+                int pass = 0, kb = 0, tap = 0, cb = 0;
                 int dy = 0, dx = 0;
-                if (p.taps == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                if (p.taps == 9) { dy = -1; dx = -1; }
                 const uint32_t b_off = kABytes + (p.cluster > 1 ? crank * (Cfg::kBBytes >> cshift) : 0);
                 const int b_row = n0 + (p.cluster > 1 ? crank * (BN >> cshift) : 0);
-                for (int kbg = p.kb_begin; kbg < p.kb_end; ++kbg) {
+                for (int kbg = 0; kbg < p.nkb; ++kbg) {
                     const CUtensorMap* ta = &p.tmA[pass_a(pass)];
                     const int bsel = pass_b(pass);
                     const CUtensorMap* tb = &p.tmB[bsel];
@@ -336,24 +343,30 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         // ======================= MMA issuer, halo mode =======================
         constexpr uint32_t idesc = (1u << 4) | kFmtBits | (uint32_t(BN >> 3) << 17) |
                                    (uint32_t((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
-        int stage = 0, bs = 0, it = 0;
+        int stage = 0, bs = 0, gs = 0;                          // gs = running segment count: accumulator gs & 1
         uint32_t phase = 0, bphase = 0;
         const bool issuer = !PAIR || crank == 0;                // pair mode: the leader issues for both CTAs
         if (issuer && p.resb && unit0 < p.num_units) {
             mbar_wait(bar_bres, 0, p.err_flag);
             tc_fence_after();
         }
-        for (int unit = unit0; issuer && unit < p.num_units; unit += ustep, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BN;
+        for (int unit = unit0; issuer && unit < p.num_units; unit += ustep) {
+            uint32_t tmem_d = 0;
+            int seg_left = 0, as = 0;                           // channel blocks left in the open segment
             // The per-tap work is kept to a handful of uniform instructions: all 9 tap views are constant offsets
             // of ONE descriptor (fully unrolled), and with resident weights the 36 MMAs of a channel block are
             // issued from a single elected region.  (The first version rebuilt descriptors and re-elected per tap
             // in a rolled loop: ~500 cycles of issue overhead per tap, 4x the MMA time at N = 64.)
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                if (seg_left == 0) {                                        // open the next accumulation segment
+                    as = gs & 1;
+                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs >> 1) & 1u) ^ 1u, p.err_flag);
+                    tc_fence_after();
+                    tmem_d = tmem_base + as * BN;
+                    seg_left = p.seg_len;
+                    ++gs;
+                }
+                const int first = (seg_left == p.seg_len) ? 0 : 1;          // 0: this channel block starts the chain
                 mbar_wait(bar_full + 8 * stage, phase, p.err_flag);         // halo tile landed
                 tc_fence_after();
                 const uint64_t da0 = make_halo_desc(stage_base + stage * kHaloBytes);
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                                 const uint64_t db = db0 + (uint64_t)(tap * bstep);
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)
-                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k | plane) != 0 ? 1u : 0u);
+                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
                             }
                         }
                         commit(bar_empty + 8 * stage);                 // halo tile free again
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)
-                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k | plane) != 0 ? 1u : 0u);
+                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
                                 commit(bar_bempty + 8 * bs);
                                 if (tap == 8 && plane == p.npass - 1) commit(bar_empty + 8 * stage);
                             }
@@ -395,9 +408,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     }
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (--seg_left == 0 || cb == p.cin_blocks - 1) {            // segment complete -> epilogue adds it in
+                    seg_left = 0;
+                    if (elect_one()) commit(bar_tfull + 8 * as);
+                    __syncwarp();
+                }
             }
-            if (elect_one()) commit(bar_tfull + 8 * as);
-            __syncwarp();
         }
     } else if (warp == 1 && PAIR) {
         // ======================= MMA issuer, pair mode: rank 0 issues M = 256 MMAs for both CTAs =======
@@ -406,30 +422,32 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                                        (uint32_t((2 * kTileM) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int unit = unit0; unit < p.num_units; unit += ustep, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);    // both CTAs' epilogues drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // both CTAs' TMA bytes landed
+            int gs = 0;
+            for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
+                    const int as = gs & 1;
+                    const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
+                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs >> 1) & 1u) ^ 1u, p.err_flag);   // both CTAs' epilogues drained it
                     tc_fence_after();
-                    const uint32_t sa = stage_base + stage * stage_pitch;
-                    const uint64_t da = make_sw128_desc(sa);
-                    const uint64_t db = make_sw128_desc(sa + kABytes);
-                    if (elect_one()) {
+                    const uint32_t tmem_d = tmem_base + as * BN;
+                    for (int kb = k0; kb < k1; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // both CTAs' TMA bytes landed
+                        tc_fence_after();
+                        const uint32_t sa = stage_base + stage * stage_pitch;
+                        const uint64_t da = make_sw128_desc(sa);
+                        const uint64_t db = make_sw128_desc(sa + kABytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
-                        umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)0x3);   // stage free again, in both CTAs
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                            umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)0x3);   // stage free again, in both CTAs
+                        }
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
+                    if (elect_one()) umma_commit_2sm(bar_tfull + 8 * as, (uint16_t)0x3);   // both epilogues may add it in
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                if (elect_one()) umma_commit_2sm(bar_tfull + 8 * as, (uint16_t)0x3);   // both epilogues may drain
-                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -439,38 +457,42 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                                        (uint32_t(kTileM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int unit = unit0; unit < p.num_units; unit += ustep, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * as, aphase ^ 1u, p.err_flag);    // epilogue drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = p.kb_begin; kb < p.kb_end; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // TMA bytes landed
+            int gs = 0;
+            for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
+                    const int as = gs & 1;
+                    const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
+                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs >> 1) & 1u) ^ 1u, p.err_flag);   // epilogue drained this accumulator
                     tc_fence_after();
-                    const uint32_t sa = stage_base + stage * stage_pitch;
-                    const uint64_t da = make_sw128_desc(sa);
-                    const uint64_t db = make_sw128_desc(sa + kABytes);
-                    if (elect_one()) {
+                    const uint32_t tmem_d = tmem_base + as * BN;
+                    for (int kb = k0; kb < k1; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // TMA bytes landed
+                        tc_fence_after();
+                        const uint32_t sa = stage_base + stage * stage_pitch;
+                        const uint64_t da = make_sw128_desc(sa);
+                        const uint64_t db = make_sw128_desc(sa + kABytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > p.kb_begin || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+                                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                            }
+                            // frees the smem stage when the MMAs retire — in cluster mode on BOTH CTAs: the peer's
+                            // producer multicasts into this stage too and must see it released
+                            if (p.cluster > 1) umma_commit_multicast(bar_empty + 8 * stage, cmask);
+                            else umma_commit(bar_empty + 8 * stage);
                         }
-                        // frees the smem stage when the MMAs retire — in cluster mode on BOTH CTAs: the peer's
-                        // producer multicasts into this stage too and must see it released
-                        if (p.cluster > 1) umma_commit_multicast(bar_empty + 8 * stage, cmask);
-                        else umma_commit(bar_empty + 8 * stage);
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
+                    if (elect_one()) umma_commit(bar_tfull + 8 * as);       // segment complete -> epilogue adds it in
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                if (elect_one()) umma_commit(bar_tfull + 8 * as);           // accumulator complete -> epilogue
-                __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ======================= epilogue =======================
         // Thread = one accumulator row (pixel); a chunk = 32 output channels held in registers.
         // 2x2 pooling never leaves the warp: the tile box is at most 16 pixels wide, so a warp holds an
@@ -486,10 +508,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         const int t2 = row / p.BW;
         const int hh = t2 % p.BH;
         const int bb = t2 / p.BH;
-        int it = 0;
-        for (int unit = unit0; unit < p.num_units; unit += ustep, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
+        constexpr int NC = BN / 64;                  // 32-column chunks per thread: chunk index c = grp + 2 * ci
+        int gs = 0;                                  // running segment count (same sequence as the MMA warp's)
+        for (int unit = unit0; unit < p.num_units; unit += ustep) {
             int m, n0;
             unit_tile(unit, m, n0);
             const int wt = m % p.tiles_w; m /= p.tiles_w;
@@ -498,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             const int x = wt * p.BW + ww, y = ht * p.BH + hh, b = bt * p.BB + bb;
             bool valid;
             size_t obase;
-            if (p.pool && !p.raw) {
+            if (p.pool) {
                 const int px = x >> 1, py = y >> 1;
                 valid = px < p.Wo && py < p.Ho && b < p.B;          // all 4 lanes of a window store (8 channels each)
                 obase = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + n0;
@@ -507,52 +528,49 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 obase = ((size_t(b) * p.Ho + y) * p.Wo + x) * p.N + n0;
             }
 
-            mbar_wait(bar_tfull + 8 * as, aphase, p.err_flag);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN;
-
-#pragma unroll 1
-            for (int c = grp; c < BN / 32; c += 2) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                if (c + 2 >= BN / 32) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * as, 0));   // the leader's MMA warp waits
-                        else mbar_arrive(bar_tempty + 8 * as);
-                    }
-                }
-                float v[32];
-                if (p.raw) {
-                    // exact-accumulation path: un-biased fp32 partial sums of this K segment, summed in fp32
-                    // round-to-nearest across segments (the tensor core's own accumulation truncates)
-                    if (valid) {
-                        float4* d = reinterpret_cast<float4*>(p.out_f32 + obase + c * 32);
+            // ---- add the tile's accumulation segments in fp32 registers (round-to-nearest): run[ci][j] = this row's
+            // column n0 + 32 * (grp + 2 ci) + j.  A segment's accumulator goes back to the MMA warp as soon as it has
+            // been read, so the tensor pipe runs the next segment while this one is being added.
+            float run[NC][32];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 t = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                            if (p.raw == 2) {
-                                const float4 o4 = d[q];
-                                t.x += o4.x; t.y += o4.y; t.z += o4.z; t.w += o4.w;
-                            }
-                            d[q] = t;
-                        }
-                    }
-                    continue;
+            for (int ci = 0; ci < NC; ++ci)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) run[ci][j] = 0.f;
+#pragma unroll 1
+            for (int seg = 0; seg < p.nseg; ++seg, ++gs) {
+                const int as = gs & 1;
+                mbar_wait(bar_tfull + 8 * as, ((uint32_t)gs >> 1) & 1u, p.err_flag);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN + grp * 32;
+#pragma unroll
+                for (int ci = 0; ci < NC; ++ci) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + ci * 64, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * as, 0));   // the leader's MMA warp waits
+                    else mbar_arrive(bar_tempty + 8 * as);
+                }
+            }
+
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+                const int c = grp + 2 * ci;
+                float (&v)[32] = run[ci];
                 {
                     const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 bv = bp[q];
-                        v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bv.x;
-                        v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bv.y;
-                        v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bv.z;
-                        v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bv.w;
+                        v[4 * q + 0] += bv.x;
+                        v[4 * q + 1] += bv.y;
+                        v[4 * q + 2] += bv.z;
+                        v[4 * q + 3] += bv.w;
                     }
                 }
                 if (p.relu) {
@@ -652,70 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Finishing kernel of the exact-accumulation path: raw fp32 sums [B,H,W,N] -> +bias -> ReLU -> 2x2 pool
-// -> bf16 hi/lo (or fp32).  One thread per (output pixel, 8 channels).
-// ------------------------------------------------------------------------------------------------
-constexpr int kExactSegment = 16;   // K-blocks (= 64 MMAs of K = 16) per accumulation chain
-
-__global__ void __launch_bounds__(256) finish_layer_kernel(const float* __restrict__ raw, int B, int H, int W, int N,
-                                                           const float* __restrict__ bias, int relu, int pool,
-                                                           __nv_bfloat16* __restrict__ out_hi,
-                                                           __nv_bfloat16* __restrict__ out_lo,
-                                                           float* __restrict__ out_f32) {
-    const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
-    const int ng = N / 8;
-    const size_t items = size_t(B) * Ho * Wo * ng;
-    for (size_t it = blockIdx.x * size_t(blockDim.x) + threadIdx.x; it < items; it += size_t(gridDim.x) * blockDim.x) {
-        const int g = int(it % ng);
-        size_t px = it / ng;
-        const int x = int(px % Wo); px /= Wo;
-        const int y = int(px % Ho);
-        const int b = int(px / Ho);
-        float bv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bv[j] = bias ? __ldg(bias + g * 8 + j) : 0.f;
-        float v[8];
-        auto load = [&](int yy, int xx, float (&t)[8]) {
-            const float4* s4 = reinterpret_cast<const float4*>(raw + ((size_t(b) * H + yy) * W + xx) * N + g * 8);
-            const float4 a = s4[0], c = s4[1];
-            t[0] = a.x + bv[0]; t[1] = a.y + bv[1]; t[2] = a.z + bv[2]; t[3] = a.w + bv[3];
-            t[4] = c.x + bv[4]; t[5] = c.y + bv[5]; t[6] = c.z + bv[6]; t[7] = c.w + bv[7];
-            if (relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], 0.f);
-            }
-        };
-        if (!pool) {
-            load(y, x, v);
-        } else {
-            float t0[8], t1[8], t2[8], t3[8];
-            load(2 * y, 2 * x, t0); load(2 * y, 2 * x + 1, t1); load(2 * y + 1, 2 * x, t2); load(2 * y + 1, 2 * x + 1, t3);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                v[j] = pool == 1 ? fmaxf(fmaxf(t0[j], t1[j]), fmaxf(t2[j], t3[j])) : ((t0[j] + t1[j]) + (t2[j] + t3[j])) * 0.25f;
-        }
-        const size_t o = ((size_t(b) * Ho + y) * Wo + x) * N + g * 8;
-        if (out_f32) {
-            float4* d = reinterpret_cast<float4*>(out_f32 + o);
-            d[0] = make_float4(v[0], v[1], v[2], v[3]);
-            d[1] = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-            uint4 hi;
-            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(out_hi + o) = hi;
-            if (out_lo) {
-                uint4 lo;
-                lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-                lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-                lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-                lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-                *reinterpret_cast<uint4*>(out_lo + o) = lo;
-            }
-        }
-    }
-}
+constexpr int kSegmentBlocks = 16;  // K blocks (= 64 MMAs of K = 16) per accumulation chain in tensor memory
 
 // ------------------------------------------------------------------------------------------------
 // Host side
@@ -888,8 +843,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         struct Plan { int halo, resb, b_stages, stages, smem; };
         auto plan = [&](int b_bytes) {
             Plan r;
-            const int res = (pp.kb_end - pp.kb_begin) * b_bytes;
-            if (pp.halo && pp.raw == 0) {
+            const int res = pp.nkb * b_bytes;
+            if (pp.halo) {
                 r.halo = 1;
                 r.resb = (h->resident_b && pp.tiles_n == 1 && res + 2 * kHaloBytes <= budget) ? 1 : 0;
                 if (r.resb) {
@@ -930,7 +885,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         // gemm_cluster = 1: when every CTA pair gets work; 2 (tests): whenever the layer has two M tiles;
         // 3: only layers with many M tiles per CTA
         const bool pair_mode = h->gemm_twocta && cs == 2;
-        if (h->gemm_cluster && (!pp.halo || (pair_mode && h->gemm_pair_halo)) && pp.raw == 0 && npass <= 2 && num_m >= 2 &&
+        if (h->gemm_cluster && (!pp.halo || (pair_mode && h->gemm_pair_halo)) && num_m >= 2 &&
             (h->gemm_cluster == 2 || (h->gemm_cluster == 1 && pair_units >= h->sm_count / cs) ||
              (h->gemm_cluster == 3 && num_m >= 2 * h->sm_count))) {
             pp.cluster = cs;
@@ -938,10 +893,10 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             if (pair_mode) { pp.twocta = 1; apply(pair); smem = pair.smem; }
             g = cs * (h->sm_count / cs);
             if (encode_weight_map(&pp.tmBh[0], L.w_hi, L.K, L.N, BN / cs, f16) != FADB_OK ||
-                (npass == 2 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16) != FADB_OK)) {
+                (npass >= 2 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16) != FADB_OK)) {
                 pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; pp.twocta = 0; apply(plain); smem = plain.smem;
             }
-            if (npass != 2) pp.tmBh[1] = pp.tmBh[0];
+            if (npass < 2) pp.tmBh[1] = pp.tmBh[0];
         }
         void (*kern)(GemmParams);
         void (*kern_pair)(GemmParams);
@@ -1008,38 +963,18 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         launch_err = cudaLaunchKernelEx(&cfg, kern, pp);
         h->launches++;
     };
-    const int nk = npass * io.taps * p.cin_blocks;
-    if (npass <= 2) {
-        p.kb_begin = 0;
-        p.kb_end = nk;
-        p.raw = 0;
-        launch(p);
+    // accumulation segments (GemmParams::nseg): chains of at most kSegmentBlocks K blocks (64 MMAs); in halo mode a
+    // segment is a whole number of channel blocks (9 * npass K blocks each)
+    p.nkb = npass * io.taps * p.cin_blocks;
+    if (halo) {
+        p.seg_len = kSegmentBlocks / (9 * npass) > 0 ? kSegmentBlocks / (9 * npass) : 1;
+        p.nseg = (p.cin_blocks + p.seg_len - 1) / p.seg_len;
     } else {
-        // bf16x3 "exact accumulation": the fp32 accumulator inside tcgen05.mma truncates (error grows linearly
-        // with the chain length: 5e-6 relative at K = 4608), so K is cut into segments of kExactSegment
-        // K-blocks; each launch leaves raw fp32 partial sums, added in fp32 round-to-nearest, and a small
-        // finishing kernel applies bias / ReLU / pooling and the hi/lo split.
-        const size_t scratch_elems = size_t(io.B) * io.H * io.W * L.N;
-        FADB_CHECK(h->ws_misc.reserve(scratch_elems * sizeof(float)));
-        GemmParams q = p;
-        q.out_f32 = h->ws_misc.as<float>();
-        q.out_hi = nullptr; q.out_lo = nullptr;
-        q.Ho = io.H; q.Wo = io.W;
-        int seg = 0;
-        for (int k0 = 0; k0 < nk; k0 += kExactSegment, ++seg) {
-            q.kb_begin = k0;
-            q.kb_end = (k0 + kExactSegment < nk) ? k0 + kExactSegment : nk;
-            q.raw = seg == 0 ? 1 : 2;
-            launch(q);
-        }
-        const size_t out_px = size_t(io.B) * p.Ho * p.Wo;
-        const size_t items = out_px * (L.N / 8);
-        int fg = (int)((items + 255) / 256);
-        if (fg > 148 * 16) fg = 148 * 16;
-        finish_layer_kernel<<<fg, 256, 0, st>>>(h->ws_misc.as<float>(), io.B, io.H, io.W, L.N, L.bias, io.relu, io.pool,
-                                                 p.out_hi, p.out_lo, p.out_f32);
-        h->launches++;
+        p.nseg = (p.nkb + kSegmentBlocks - 1) / kSegmentBlocks;
+        p.seg_len = (p.nkb + p.nseg - 1) / p.nseg;
+        p.nseg = (p.nkb + p.seg_len - 1) / p.seg_len;
     }
+    launch(p);
     FADB_CUDA_CHECK(launch_err);
     if (h->profile) {
         FADB_CUDA_CHECK(cudaEventRecord(ev1, st));

@@ -141,7 +141,9 @@ def test_cta_pair_modes_match_plain_launch(vgg_sd, monkeypatch, mode, prec):
         b = (torch.randn(Cout, generator=g) * 0.1).cuda()
         a = plain.debug_conv_layer(x, w, b, k, bool(relu), pool).cpu().numpy()
         c = paired.debug_conv_layer(x, w, b, k, bool(relu), pool).cpu().numpy()
-        assert relerr(c, a) < 1e-6, (mode, case)
+        # same K order per output row; the two-pass mode walks (tap, plane) in a different order when the pair's half
+        # weight slab fits in shared memory (resident) and the single CTA's does not (ring): fp32 re-association only
+        assert relerr(c, a) < (1e-6 if prec == "bf16" else 5e-6), (mode, case)
     feats = torch.randn(37, 96, 64, generator=torch.Generator().manual_seed(5)).cuda() * 2.0
     assert relerr(paired.embed_features(feats).cpu().numpy(), plain.embed_features(feats).cpu().numpy()) < 1e-5
 
