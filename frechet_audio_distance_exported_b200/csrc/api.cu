@@ -300,6 +300,7 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
         io.B = B; io.H = steps[i].H; io.W = steps[i].W; io.Cin = steps[i].Cin;
         io.taps = 9; io.relu = 1; io.pool = steps[i].pool;
         io.out_hi = a[cur]; io.out_lo = l[cur];
+        io.use_lo_weights = (h->x2_mask >> i) & 1u;
         FADB_CHECK(launch_gemm_layer(h, h->layers[i], io, st));
         in_hi = a[cur]; in_lo = l[cur];
         cur ^= 1;
@@ -313,6 +314,7 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
         io.taps = 1; io.relu = (i < 2); io.pool = 0;
         if (i < 2) { io.out_hi = a[cur]; io.out_lo = l[cur]; }
         else io.out_f32 = emb;                                                          // no final ReLU, vggish.py:76-77
+        io.use_lo_weights = (h->x2_mask >> (5 + i)) & 1u;
         FADB_CHECK(launch_gemm_layer(h, h->layers[5 + i], io, st));
         in_hi = a[cur]; in_lo = l[cur];
         cur ^= 1;
@@ -383,6 +385,7 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
             io.taps = 9; io.relu = 1;
             io.pool = (cv == 2 && blk < 6) ? 2 : 0;                                     // avg_pool2d, pann.py:192,255-260
             io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+            io.use_lo_weights = (h->x2_mask >> li) & 1u;
             FADB_CHECK(launch_gemm_layer(h, h->layers[li], io, st));
             C = h->layers[li].N;
             ++li;
@@ -476,6 +479,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_PAIR_HALO")) h->gemm_pair_halo = atoi(e);
     if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
+    if (const char* e = getenv("FADB_X2_MASK")) h->x2_mask = (unsigned)strtoul(e, nullptr, 0);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
     if (rc == FADB_OK) rc = frechet_init(h);

@@ -119,6 +119,7 @@ struct fadb_handle {
     int gemm_cluster_size = 2;      // CTAs per cluster: 2 or 4
     int gemm_pair_halo = 1;         // CTA pairs for the halo-mode layers too (CNN14 blocks 1-4: +10 %)
     int gemm_twocta = 1;            // clusters of 2: 1 = cta_group::2 MMAs (M = 256 across the pair) instead of weight multicast
+    unsigned x2_mask = 0xffffffffu; // fp16x2: bit i = tensor-core layer i multiplies the lo weight plane too (FADB_X2_MASK)
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;
     int64_t launches = 0;
@@ -199,6 +200,7 @@ struct LayerIO {
     __nv_bfloat16* out_hi = nullptr;
     __nv_bfloat16* out_lo = nullptr;           // may be null
     float* out_f32 = nullptr;                  // if set, fp32 output instead of bf16
+    int use_lo_weights = 1;                    // fp16x2: 0 = this layer runs single-pass (FADB_X2_MASK sensitivity sweeps)
 };
 int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, cudaStream_t st);
 int gemm_init(fadb_handle* h);

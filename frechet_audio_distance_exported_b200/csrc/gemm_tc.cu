@@ -373,12 +373,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (p.resb) {
                     const uint32_t bstep = (uint32_t)(p.cin_blocks * kBTile) >> 4;   // next tap, same channel block
                     if (elect_one()) {
-                        for (int plane = 0; plane < p.npass; ++plane) {              // fp16x2: hi weights, then lo weights
-                            const uint64_t db0 = make_sw128_desc(base + (plane * kb_per_pass + cb) * kBTile);
+                        // (tap, plane) order like the weight-ring path below: a layer's accumulation order — and with it
+                        // every bit of its output — is the same whichever path the batch size selects
+                        const uint64_t db0 = make_sw128_desc(base + cb * kBTile);
+                        const uint32_t pstep = (uint32_t)(kb_per_pass * kBTile) >> 4;    // hi plane -> lo plane (fp16x2)
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
-                                const uint64_t db = db0 + (uint64_t)(tap * bstep);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
+                            for (int plane = 0; plane < p.npass; ++plane) {
+                                const uint64_t db = db0 + (uint64_t)(tap * bstep + plane * pstep);
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)
                                     mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
@@ -746,7 +749,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                  "again after fadb_set_precision", L.f16 ? "fp16" : "bf16", f16 ? "fp16" : "bf16");
     // operand passes over K (see GemmParams::npass)
     const int npass = (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3
-                      : (h->precision == FADB_PREC_FP16X2 && L.w_lo) ? 2 : 1;
+                      : (h->precision == FADB_PREC_FP16X2 && L.w_lo && io.use_lo_weights) ? 2 : 1;
     const int BN = (L.N % 256 == 0) ? 256 : (L.N % 128 == 0 ? 128 : 64);
     FADB_REQUIRE(L.N % BN == 0 && L.N >= 64, "Cout=%d must be a multiple of 64", L.N);
     FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
