@@ -90,10 +90,19 @@ __global__ void frechet_prepare_kernel(const double* __restrict__ s1, const doub
 // ------------------------------------------------------------------------------------------------
 // DGEMM  C = alpha * op(A) * op(B) + beta * C   (row-major, 64x64x16 tiles, 4x4 per thread)
 // ------------------------------------------------------------------------------------------------
+// dyn (optional, device): the rank r found by the Cholesky step; dyn_mask bit 0 -> M = r, bit 1 -> N = r (the grid is
+// sized for the largest case and surplus tiles leave at once: no host round trip for a data-dependent dimension)
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
                                                     int lda, const double* __restrict__ B, int ldb, double beta,
-                                                    double* __restrict__ C, int ldc, int lower_only) {
+                                                    double* __restrict__ C, int ldc, int lower_only,
+                                                    const int* __restrict__ dyn, int dyn_mask) {
+    if (dyn) {
+        const int r = *dyn;
+        if (dyn_mask & 1) M = r;
+        if (dyn_mask & 2) N = r;
+    }
+    if ((int)blockIdx.y * 64 >= M || (int)blockIdx.x * 64 >= N) return;
     if (lower_only && blockIdx.x > blockIdx.y) return;      // tile strictly above the diagonal
     __shared__ __align__(16) double sA[16][64 + 2];
     __shared__ __align__(16) double sB[16][64 + 2];
@@ -167,10 +176,11 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
 
 template <bool TA, bool TB>
 static void dgemm(fadb_handle* h, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
-                  double beta, double* C, int ldc, int lower_only, cudaStream_t st) {
+                  double beta, double* C, int ldc, int lower_only, cudaStream_t st, const int* dyn = nullptr,
+                  int dyn_mask = 0) {
     if (M <= 0 || N <= 0) return;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    dgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+    dgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, dyn, dyn_mask);
     h->launches++;
 }
 
@@ -244,13 +254,51 @@ __global__ void tril_kernel(double* __restrict__ A, int d) {
         if (j > i) A[e] = 0.0;
     }
 }
-__global__ void symmetrize_kernel(double* __restrict__ A, int d) {
-    const size_t total = (size_t)d * d;
+// Rank compaction.  The semi-definite Cholesky leaves a ZERO column for every pivot below the tolerance, so a covariance of
+// N < d embeddings (BASELINE configs[1]: N = 1000, d = 2048 -> rank 999) has only r = N - 1 non-zero columns, and
+// L^T S2 L is non-zero only in those r rows / columns.  The columns are gathered to the left (Lc: d x r) and everything
+// downstream works on r instead of d: the products shrink to d*d*r + r*d*r and the tridiagonalisation to r^3.
+// rank_scan: one CTA; idx[c] = c-th column with a non-zero diagonal, meta[0] = r.
+__global__ void __launch_bounds__(1024) rank_scan_kernel(const double* __restrict__ L, int d, int* __restrict__ idx,
+                                                         int* __restrict__ meta) {
+    __shared__ int s_cnt[1024];
+    const int per = (d + 1023) / 1024;
+    const int j0 = threadIdx.x * per;
+    int c = 0;
+    for (int j = j0; j < j0 + per && j < d; ++j) c += (L[(size_t)j * d + j] != 0.0);
+    s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                    // inclusive scan
+        const int v = (threadIdx.x >= o) ? s_cnt[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_cnt[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int pos = s_cnt[threadIdx.x] - c;
+    for (int j = j0; j < j0 + per && j < d; ++j)
+        if (L[(size_t)j * d + j] != 0.0) idx[pos++] = j;
+    if (threadIdx.x == 1023) meta[0] = s_cnt[1023];
+}
+// Lc[i][c] = L[i][idx[c]] for c < r (row-major, leading dimension d); columns >= r are left untouched (never read)
+__global__ void rank_gather_kernel(const double* __restrict__ L, int d, const int* __restrict__ idx,
+                                   const int* __restrict__ meta, double* __restrict__ Lc) {
+    const int r = meta[0];
+    const size_t total = (size_t)d * r;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(e / d), j = (int)(e % d);
+        const int i = (int)(e / r), c = (int)(e % r);
+        const int j = idx[c];
+        Lc[(size_t)i * d + c] = (j <= i) ? L[(size_t)i * d + j] : 0.0;      // lower triangle only (upper is stale)
+    }
+}
+
+__global__ void symmetrize_kernel(double* __restrict__ A, int d, const int* __restrict__ meta) {
+    const int n = meta ? meta[0] : d;                      // active size (leading dimension stays d)
+    const size_t total = (size_t)n * n;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e % n);
         if (j > i) {
-            const double v = 0.5 * (A[e] + A[(size_t)j * d + i]);
-            A[e] = v;
+            const double v = 0.5 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
+            A[(size_t)i * d + j] = v;
             A[(size_t)j * d + i] = v;
         }
     }
@@ -264,7 +312,8 @@ __global__ void symmetrize_kernel(double* __restrict__ A, int d) {
 // ------------------------------------------------------------------------------------------------
 // NOTE: no __restrict__ / read-only-cache loads on A and the vectors here — inside the persistent kernel they are
 // written by other CTAs one grid barrier earlier, so they must be read through the coherent L2 path (__ldcg).
-__device__ __forceinline__ void tridiag_step(double* A, int d, int k, const double* vec_in, double* vec_out,
+// d = active matrix size, ld = leading dimension of A (row stride)
+__device__ __forceinline__ void tridiag_step(double* A, int d, int ld, int k, const double* vec_in, double* vec_out,
                                              double* diag, double* off, double* tsm, double* red) {
     double* sv = tsm;            // v_k          [d]
     double* sw = tsm + d;        // w_k          [d]
@@ -288,7 +337,7 @@ __device__ __forceinline__ void tridiag_step(double* A, int d, int k, const doub
 
     // (b) updated row r -> diag[r], x = row[r+1:], next reflector
     const double vr = sv[r], wr = sw[r];
-    const double* Ar = A + (size_t)r * d;
+    const double* Ar = A + (size_t)r * ld;
     part = 0.0;
     for (int c = r + 1 + tid; c < d; c += nt) {
         const double x = fma(-vr, sw[c], fma(-wr, sv[c], __ldcg(Ar + c)));
@@ -331,10 +380,10 @@ __device__ __forceinline__ void tridiag_step(double* A, int d, int k, const doub
     // L1 anyway (__ldcg): L1 is not coherent across SMs and this runs inside a persistent kernel
     for (int row = blockIdx.x * nwarp + warp; row < d; row += gridDim.x * nwarp) {
         if (row < first) continue;
-        double* Arow = A + (size_t)row * d;
+        double* Arow = A + (size_t)row * ld;
         const double vrow = sv[row], wrow = sw[row];
         double dot = 0.0;
-        if ((d & 1) == 0) {
+        if (((d | ld) & 1) == 0) {
             // even d: rows are 16-byte aligned -> 128-bit loads, 8 x 512 B in flight per warp (the streaming part is
             // bound by bytes in flight per SM against the L2 round trip, not by L2 bandwidth).  Starts at the even
             // column <= first; the extra column (the finished column r) is updated harmlessly, sn[r] = 0.
@@ -393,20 +442,24 @@ __device__ __forceinline__ void tridiag_step(double* A, int d, int k, const doub
 // All Householder steps in ONE cooperative launch: a grid-wide barrier separates step k (which leaves p_{k+1}
 // complete in global memory) from step k+1.  One launch per step cost ~6 us of launch + ramp per step
 // (2047 steps at d = 2048); the grid barrier costs ~2 us.
-__global__ void __launch_bounds__(512) tridiag_persistent_kernel(double* __restrict__ A, int d, double* __restrict__ vec0,
+// ld = leading dimension (and size of the vec / diag buffers); the active size is *meta (the rank found by the Cholesky
+// step, read on the device: every CTA sees the same value, so the grid-wide barriers stay matched)
+__global__ void __launch_bounds__(512) tridiag_persistent_kernel(double* __restrict__ A, int ld, double* __restrict__ vec0,
                                                                  double* __restrict__ vec1, double* __restrict__ diag,
-                                                                 double* __restrict__ off) {
+                                                                 double* __restrict__ off, const int* __restrict__ meta) {
     extern __shared__ __align__(16) double tsm[];
     __shared__ double red[33];
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int d = meta ? meta[0] : ld;
     int step = 0;
     for (int k = -1; k <= d - 3; ++k, ++step) {
+        // the vector buffers keep their [v (ld) | p (ld) | beta] layout
         const double* vin = (step & 1) ? vec1 : vec0;
         double* vout = (step & 1) ? vec0 : vec1;
-        tridiag_step(A, d, k, vin, vout, diag, off, tsm, red);
+        tridiag_step(A, d, ld, k, vin, vout, diag, off, tsm, red);
         grid.sync();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) diag[d - 1] = A[(size_t)(d - 1) * d + (d - 1)];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d >= 1) diag[d - 1] = A[(size_t)(d - 1) * ld + (d - 1)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,7 +475,10 @@ __global__ void __launch_bounds__(512) tridiag_persistent_kernel(double* __restr
 // Fixed 56 halvings of [-1-delta, 1+delta] -> absolute accuracy ~4e-17 * radius, all that tr sqrt needs.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) bisect_kernel(const double* __restrict__ diag, const double* __restrict__ off,
-                                                     int d, double* __restrict__ scal, double* __restrict__ eig_out) {
+                                                     int dmax, double* __restrict__ scal, double* __restrict__ eig_out,
+                                                     const int* __restrict__ meta) {
+    const int d = meta ? meta[0] : dmax;                   // active size (the rank), device-resident
+    if (d <= 0) return;                                    // S1 = 0: tr sqrt(S1 S2) = 0 (scal[2] stays 0)
     extern __shared__ __align__(16) double bsm[];
     double* sa = bsm;          // [d]  a / radius
     double* se2 = bsm + d;     // [d]  (off / radius)^2 ; se2[j] couples j and j+1
@@ -524,8 +580,8 @@ int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const do
                    double* out, cudaStream_t st) {
     FADB_REQUIRE(d >= 1 && d <= 8192, "Frechet: d=%d out of range", d);
     const size_t dd = (size_t)d * d;
-    // workspace: A (d*d) | B (d*d) | T (d*d) | vec ping-pong 2*(2d+1) | diag d | off d | scal 8 | eig d
-    const size_t need = (3 * dd + 2 * (2 * (size_t)d + 1) + 3 * (size_t)d + 8) * sizeof(double);
+    // workspace: A (d*d) | B (d*d) | T (d*d) | vec ping-pong 2*(2d+1) | diag d | off d | eig d | scal 8 | idx d ints | meta
+    const size_t need = (3 * dd + 2 * (2 * (size_t)d + 1) + 3 * (size_t)d + 8) * sizeof(double) + ((size_t)d + 4) * sizeof(int);
     FADB_CHECK(h->ws_frechet.reserve(need));
     double* A = h->ws_frechet.as<double>();
     double* B = A + dd;
@@ -557,16 +613,20 @@ int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const do
             dgemm<false, true>(h, rem, rem, nb, -1.0, P, d, P, d, 1.0, A22, d, /*lower_only=*/1, st);
         }
     }
-    tril_kernel<<<g, 256, 0, st>>>(A, d);
+    // ---- rank compaction: Lc = the r non-zero columns of L, gathered to the left (r = d for a full-rank S1)
+    int* idx = reinterpret_cast<int*>(scal + 8);
+    int* meta = idx + d;
+    rank_scan_kernel<<<1, 1024, 0, st>>>(A, d, idx, meta);
+    rank_gather_kernel<<<g, 256, 0, st>>>(A, d, idx, meta, T);
+    h->launches += 2;
+
+    // ---- M = Lc^T (S2 Lc): r x r, leading dimension d
+    dgemm<false, false>(h, d, d, d, 1.0, B, d, T, d, 0.0, A, d, 0, st, meta, 2);     // A = S2 Lc       (d x r)
+    dgemm<true, false>(h, d, d, d, 1.0, T, d, A, d, 0.0, B, d, 0, st, meta, 3);      // B = Lc^T A      (r x r)
+    symmetrize_kernel<<<g, 256, 0, st>>>(B, d, meta);
     h->launches++;
 
-    // ---- M = L^T (S2 L)
-    dgemm<false, false>(h, d, d, d, 1.0, B, d, A, d, 0.0, T, d, 0, st);      // T = S2 L
-    dgemm<true, false>(h, d, d, d, 1.0, A, d, T, d, 0.0, B, d, 0, st);       // B = L^T T
-    symmetrize_kernel<<<g, 256, 0, st>>>(B, d);
-    h->launches++;
-
-    // ---- tridiagonalise B
+    // ---- tridiagonalise B (active size r)
     FADB_CUDA_CHECK(cudaMemsetAsync(vec0, 0, 2 * (2 * (size_t)d + 1) * sizeof(double), st));
     {
         const size_t smem = 3 * (size_t)d * sizeof(double);
@@ -575,13 +635,14 @@ int launch_frechet(fadb_handle* h, const double* mu1, const double* s1, const do
         if (grid < 1) grid = 1;
         double* Bm = B;
         int dd_ = d;
-        void* args[] = {(void*)&Bm, (void*)&dd_, (void*)&vec0, (void*)&vec1, (void*)&diag, (void*)&off};
+        const int* mp = meta;
+        void* args[] = {(void*)&Bm, (void*)&dd_, (void*)&vec0, (void*)&vec1, (void*)&diag, (void*)&off, (void*)&mp};
         FADB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tridiag_persistent_kernel, dim3(grid), dim3(512), args,
                                                     smem, st));
         h->launches++;
     }
     // ---- eigenvalues + trace of the square root
-    bisect_kernel<<<(d + 127) / 128, 128, 2 * (size_t)d * sizeof(double), st>>>(diag, off, d, scal, eig);
+    bisect_kernel<<<(d + 127) / 128, 128, 2 * (size_t)d * sizeof(double), st>>>(diag, off, d, scal, eig, meta);
     h->launches++;
     frechet_combine_kernel<<<1, 256, 0, st>>>(mu1, mu2, d, scal, out, h->err_flag);
     h->launches++;

@@ -43,6 +43,7 @@ struct FrontParams {
     const int* band_len;
     const float* band_wt;   // transposed band weights (FrontTables::band_wt), staged in shared memory by the kernels
     int wt_rows, wt_off1;
+    double win_rot_c, win_rot_s;   // cos / sin of 2 pi 64 / win_len: the Hann window advances 64 samples per register slot
     float* out;         // [n_clips][rows_out][64]
 };
 
@@ -110,25 +111,43 @@ struct FftPlan {
     static constexpr int kSlots = offset(kNumPasses) * 32;              // double2 entries
 };
 
+// Per-lane constants of the front end, held in REGISTERS for the whole kernel.  ncu (profiles/r02_ncu_front.json) shows the
+// kernel bound by shared-memory wavefronts (LSU data pipe 78 % busy, fp64 pipe 18 %); a fifth of those wavefronts were
+// per-frame reloads of constants that depend on the lane only: the pass twiddles (7 + 6 double2 per lane), the split
+// twiddles (5) and the window (8).  They are now derived per frame from one BASE value each with a few fp64
+// multiplications: w^r = w^(r-1) * w for the radix-R butterfly inputs, w_(k+32) = w_k * W^32 for the split, and a
+// rotation by 64 samples for the Hann window (cos / sin recurrence; at most 8 steps, ~1e-15 absolute).
+template <int M>
+struct LaneConsts {
+    static constexpr int kBases = (M == 256) ? 3 : 4;       // sum over passes >= 1 of butterflies per lane
+    double2 pb[kBases];     // pass twiddle bases: exp(-2 pi i (i & (pp-1)) tstep / NF) of butterfly i = lane + 32 q
+    double2 sb;             // split twiddle base exp(-2 pi i lane / NF)
+    double wc[2], ws[2];    // cos / sin of 2 pi n / win_len for n = 2 lane, 2 lane + 1
+};
+template <int NF> struct SplitStep;      // exp(-2 pi i 32 / NF)
+template <> struct SplitStep<256> { static constexpr double c = 0.70710678118654752440, s = -0.70710678118654752440; };
+template <> struct SplitStep<512> { static constexpr double c = 0.92387953251128675613, s = -0.38268343236508977173; };
+template <> struct SplitStep<1024> { static constexpr double c = 0.98078528040323044913, s = -0.19509032201612826785; };
+
 template <int M, int NF>
-__device__ __forceinline__ void build_pass_twiddles(double2* __restrict__ ptw, const double2* __restrict__ tw_global) {
+__device__ __forceinline__ void build_lane_consts(LaneConsts<M>& lc, const double2* __restrict__ tw_global, int win_len,
+                                                  int lane) {
     using P = FftPlan<M>;
-    int pp = P::radix(0);
+    int pp = P::radix(0), slot = 0;
 #pragma unroll
     for (int ps = 1; ps < P::kNumPasses; ++ps) {
-        const int R = P::radix(ps), PER = P::per(ps), T = M / R;
+        const int R = P::radix(ps), PER = P::per(ps);
         const int tstep = NF / (pp * R);
-        for (int e = threadIdx.x; e < PER * (R - 1) * 32; e += blockDim.x) {
-            const int lane = e & 31;
-            const int r = (e >> 5) % (R - 1) + 1;
-            const int q = (e >> 5) / (R - 1);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
             const int i = lane + 32 * q;
-            double2 v = make_double2(1.0, 0.0);
-            if (i < T) v = tw_global[r * (i & (pp - 1)) * tstep];
-            ptw[P::offset(ps) * 32 + e] = v;
+            lc.pb[slot++] = tw_global[(i & (pp - 1)) * tstep];
         }
         pp *= R;
     }
+    lc.sb = tw_global[lane];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) sincospi(2.0 * (double)(2 * lane + e) / (double)win_len, &lc.ws[e], &lc.wc[e]);
 }
 
 // One in-place Stockham pass of radix R over the warp's M-point buffer: every lane first pulls ALL of
@@ -136,7 +155,7 @@ __device__ __forceinline__ void build_pass_twiddles(double2* __restrict__ ptw, c
 // The FIRST pass takes its inputs from registers instead: z[j] = input element lane + 32 j (windowed PCM straight from
 // global memory).
 template <int M, int R, bool FIRST>
-__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ ptw, int pp, int lane,
+__device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2* __restrict__ pbase, int pp, int lane,
                                          const double2 (&z)[M / 32]) {
     constexpr int T = M / R;                 // butterflies in the pass
     constexpr int PER = (T + 31) / 32;       // per lane
@@ -145,6 +164,7 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
     for (int q = 0; q < PER; ++q) {
         const int i = lane + 32 * q;
         if (T >= 32 || i < T) {
+            double2 pw = FIRST ? make_double2(1.0, 0.0) : pbase[q];      // w^r of this butterfly, built up by multiplication
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 double2 v;
@@ -152,7 +172,10 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
                     v = z[q + r * PER];               // element i + r T = lane + 32 (q + r PER)
                 } else {
                     v = x[pidx(i + r * T)];
-                    if (r > 0) v = cmul(v, ptw[(q * (R - 1) + (r - 1)) * 32 + lane]);
+                    if (r > 0) {
+                        v = cmul(v, pw);
+                        if (r + 1 < R) pw = cmul(pw, pbase[q]);
+                    }
                 }
                 u[q][r] = v;
             }
@@ -207,15 +230,16 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ x, const double2*
 // complex FFT of length M (128 / 256 / 512) of the sequence held as z[j] = element lane + 32 j, result in x (padded
 // index pidx)
 template <int M>
-__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const double2* __restrict__ ptw, int lane,
+__device__ __forceinline__ void fft_inplace(double2* __restrict__ x, const LaneConsts<M>& lc, int lane,
                                             const double2 (&z)[M / 32]) {
     using P = FftPlan<M>;
     constexpr int R0 = P::radix(0), R1 = P::radix(1), R2 = P::radix(2);
     static_assert(M / P::radix(0) >= 32, "first pass: at least one butterfly per lane");
-    fft_pass<M, R0, true>(x, ptw, 1, lane, z);
-    fft_pass<M, R1, false>(x, ptw + P::offset(1) * 32, R0, lane, z);
-    fft_pass<M, R2, false>(x, ptw + P::offset(2) * 32, R0 * R1, lane, z);
-    if constexpr (P::kNumPasses == 4) fft_pass<M, P::radix(3), false>(x, ptw + P::offset(3) * 32, R0 * R1 * R2, lane, z);
+    static_assert(P::per(1) + P::per(2) + (P::kNumPasses == 4 ? P::per(3) : 0) == LaneConsts<M>::kBases, "base count");
+    fft_pass<M, R0, true>(x, lc.pb, 1, lane, z);
+    fft_pass<M, R1, false>(x, lc.pb, R0, lane, z);
+    fft_pass<M, R2, false>(x, lc.pb + P::per(1), R0 * R1, lane, z);
+    if constexpr (P::kNumPasses == 4) fft_pass<M, P::radix(3), false>(x, lc.pb + P::per(1) + P::per(2), R0 * R1 * R2, lane, z);
 }
 
 constexpr int kFrontWarps = 8;
@@ -226,14 +250,12 @@ struct FrontSmem {
     static constexpr int M = NF / 2;
     static constexpr int kBufSlots = M + M / 8 + 2;                       // padded complex buffer per warp
     static constexpr int kSpecPitch = M + 4;                              // floats per warp spectrum (M + 1 used)
-    static constexpr int kTwBytes = (M + 1) * 16;                         // split twiddles exp(-2 pi i k/NF), k = 0..M
-    static constexpr int kWinBytes = NF * 8;
-    static constexpr int kPtwBytes = FftPlan<M>::kSlots * 16;
+    // (the twiddle and window tables of round 1 are gone from shared memory: LaneConsts keeps their bases in registers)
     static constexpr int kBufBytes = kFrontWarps * kBufSlots * 16;
     static constexpr int kSpecBytes = kFrontWarps * kSpecPitch * 4;
     static constexpr int kWtRows = NF / 16;                               // >= band-weight rows of every model (checked on the host)
     static constexpr int kWtBytes = kWtRows * 32 * 4;
-    static constexpr int kTotal = kTwBytes + kWinBytes + kPtwBytes + kBufBytes + kSpecBytes + kWtBytes;
+    static constexpr int kTotal = kBufBytes + kSpecBytes + kWtBytes;
 };
 
 // One STFT frame -> 64 log-mel values, by one warp.  out_row[lane] and out_row[lane + 32] are written
@@ -241,8 +263,7 @@ struct FrontSmem {
 template <int NF, bool SPLIT = false>
 __device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView pcm, int row, int lane,
                                              double2* __restrict__ x, float* __restrict__ spec,
-                                             const double2* __restrict__ s_tw, const double* __restrict__ s_win,
-                                             const double2* __restrict__ s_ptw, const float* __restrict__ s_wt,
+                                             const LaneConsts<NF / 2>& lc, const float* __restrict__ s_wt,
                                              const int (&bst)[2], const int (&bln)[2], float* __restrict__ out_row) {
     constexpr int M = NF / 2;
     // ---- load + window (fp32 PCM x fp64 Hann, like numpy's promotion): z[n] = x[2n] + i x[2n+1]
@@ -307,12 +328,25 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView
         }
     }
     double2 z[J];
+    {   // fp32 PCM x fp64 periodic Hann 0.5 - 0.5 cos(2 pi n / win_len) (numpy's promotion), 0 past win_len; the cosine of
+        // n = 2 (lane + 32 j) + e comes from the lane's base angle by j rotations of 64 samples
+        double c0 = lc.wc[0], s0 = lc.ws[0], c1 = lc.wc[1], s1 = lc.ws[1];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {                // fp32 PCM x fp64 Hann, like numpy's promotion (s_win is 0 past win_len)
-        const double2 wn = *reinterpret_cast<const double2*>(&s_win[2 * (lane + 32 * j)]);
-        z[j] = make_double2((double)raw[j].x * wn.x, (double)raw[j].y * wn.y);
+        for (int j = 0; j < J; ++j) {
+            const int n = 2 * (lane + 32 * j);
+            const double w0 = (n < p.win_len) ? fma(-0.5, c0, 0.5) : 0.0;
+            const double w1 = (n + 1 < p.win_len) ? fma(-0.5, c1, 0.5) : 0.0;
+            z[j] = make_double2((double)raw[j].x * w0, (double)raw[j].y * w1);
+            if (j + 1 < J) {
+                const double t0 = c0 * p.win_rot_c - s0 * p.win_rot_s, t1 = c1 * p.win_rot_c - s1 * p.win_rot_s;
+                s0 = s0 * p.win_rot_c + c0 * p.win_rot_s;
+                s1 = s1 * p.win_rot_c + c1 * p.win_rot_s;
+                c0 = t0;
+                c1 = t1;
+            }
+        }
     }
-    fft_inplace<M>(x, s_ptw, lane, z);
+    fft_inplace<M>(x, lc, lane, z);
 
     // ---- real-FFT split, then |X| (VGGish, vggish.py:141) or |X|^2 (PANN, pann.py:118) in fp32.
     // Bins k and M-k come from the same pair (Z[k], Z[M-k]): X[k] = ze + w_k zo, X[M-k] = conj(ze - w_k zo), so each
@@ -322,15 +356,16 @@ __device__ __forceinline__ void frame_logmel(const FrontParams& p, const PcmView
         const float pw = fmaf(re, re, im * im);
         spec[k] = p.power_db ? pw : sqrtf(pw);
     };
+    double2 w = lc.sb;                           // exp(-2 pi i k / NF), k = lane + 32 q: advanced by W^32 per q
 #pragma unroll
     for (int q = 0; q <= M / 64; ++q) {
         const int k = lane + 32 * q;
+        if (q > 0) w = cmul(w, make_double2(SplitStep<NF>::c, SplitStep<NF>::s));
         if (k <= M / 2) {
             const double2 a = x[pidx(k)];
             const double2 bz = x[pidx((M - k) & (M - 1))];
             const double2 ze = make_double2(0.5 * (a.x + bz.x), 0.5 * (a.y - bz.y));
             const double2 zo = make_double2(0.5 * (a.y + bz.y), -0.5 * (a.x - bz.x));   // (a - conj b) / (2i)
-            const double2 w = s_tw[k];
             const double tx = w.x * zo.x - w.y * zo.y, ty = w.x * zo.y + w.y * zo.x;
             put(k, ze.x + tx, ze.y + ty);
             if (k != M / 2) put(M - k, ze.x - tx, ze.y - ty);
@@ -364,20 +399,16 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
     using S = FrontSmem<NF>;
     constexpr int M = NF / 2;
     extern __shared__ __align__(16) uint8_t fsm[];
-    double2* s_tw = reinterpret_cast<double2*>(fsm);                                        // [M + 1]
-    double* s_win = reinterpret_cast<double*>(fsm + S::kTwBytes);                           // [NF] (zero beyond win_len)
-    double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);          // per-pass twiddles
-    double2* s_buf = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes);
-    float* s_spec = reinterpret_cast<float*>(fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes + S::kBufBytes);
+    double2* s_buf = reinterpret_cast<double2*>(fsm);
+    float* s_spec = reinterpret_cast<float*>(fsm + S::kBufBytes);
     float* s_wt = s_spec + S::kSpecBytes / 4;
 
-    for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
-    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
-    build_pass_twiddles<M, NF>(s_ptw, p.tw);
     for (int i = threadIdx.x; i < p.wt_rows * 32; i += kFrontWarps * 32) s_wt[i] = p.band_wt[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LaneConsts<M> lc;
+    build_lane_consts<M, NF>(lc, p.tw, p.win_len, lane);
     double2* x = s_buf + warp * S::kBufSlots;
     float* spec = s_spec + warp * S::kSpecPitch;
     const int clip = blockIdx.y;
@@ -397,7 +428,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_frontend_kernel(cons
             out[(size_t)row * 64 + lane + 32] = 0.f;
             continue;
         }
-        frame_logmel<NF>(p, pcm, row, lane, x, spec, s_tw, s_win, s_ptw, s_wt, bst, bln, out + (size_t)row * 64);
+        frame_logmel<NF>(p, pcm, row, lane, x, spec, lc, s_wt, bst, bln, out + (size_t)row * 64);
     }
 }
 
@@ -437,10 +468,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
     using F = FusedTcSmem;
     constexpr uint32_t lbo = F::kLbo, sbo = F::kSbo;
     extern __shared__ __align__(16) uint8_t fsm[];
-    double2* s_tw = reinterpret_cast<double2*>(fsm);
-    double* s_win = reinterpret_cast<double*>(fsm + S::kTwBytes);
-    double2* s_ptw = reinterpret_cast<double2*>(fsm + S::kTwBytes + S::kWinBytes);
-    uint8_t* s_bufb = fsm + S::kTwBytes + S::kWinBytes + S::kPtwBytes;
+    uint8_t* s_bufb = fsm;
     double2* s_buf = reinterpret_cast<double2*>(s_bufb);
     float* s_spec = reinterpret_cast<float*>(s_bufb + S::kBufBytes);
     float* s_wt = s_spec + S::kSpecBytes / 4;
@@ -451,9 +479,6 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i <= M; i += kFrontWarps * 32) s_tw[i] = p.tw[i];
-    for (int i = threadIdx.x; i < NF; i += kFrontWarps * 32) s_win[i] = (i < p.win_len) ? p.win[i] : 0.0;
-    build_pass_twiddles<M, NF>(s_ptw, p.tw);
     for (int i = threadIdx.x; i < p.wt_rows * 32; i += kFrontWarps * 32) s_wt[i] = p.band_wt[i];
     // zero halo: rows 0 and 97, columns 0 and 65 (tile row r holds frame r-1, column c holds mel c-1)
     for (int i = threadIdx.x; i < 2 * F::kTilePitch; i += kFrontWarps * 32)
@@ -480,6 +505,8 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
         bst[h2] = p.band_start[lane + 32 * h2];
         bln[h2] = p.band_len[lane + 32 * h2];
     }
+    LaneConsts<M> lc;
+    build_lane_consts<M, NF>(lc, p.tw, p.win_len, lane);
     // phase-2 roles: builder thread = (window w, dy), both dx; drain warp = (TMEM lane quarter, channel half)
     const int bw = threadIdx.x & 127, bdy = threadIdx.x >> 7;
     const uint32_t a_row_off = (uint32_t)(bw >> 3) * sbo + (uint32_t)(bw & 7) * 16;
@@ -506,7 +533,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
         // ---- phase 1: 96 frames of this patch -> s_tile rows 1..96, columns 1..64 as {hi, lo} bf16 pairs
         for (int fi = 0; fi < ((dbg & 1) ? 0 : 12); ++fi) {
             const int fr = warp * 12 + fi;
-            frame_logmel<NF, true>(p, pcm, patch * 96 + fr, lane, x, spec, s_tw, s_win, s_ptw, s_wt, bst, bln,
+            frame_logmel<NF, true>(p, pcm, patch * 96 + fr, lane, x, spec, lc, s_wt, bst, bln,
                                    reinterpret_cast<float*>(&s_tile[fr + 1][1]));
         }
         __syncthreads();
@@ -786,6 +813,7 @@ int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64
     p.tw = t.tw; p.win = t.win;
     p.band_start = t.band_start; p.band_len = t.band_len;
     p.band_wt = t.band_wt; p.wt_rows = t.wt_rows; p.wt_off1 = t.wt_off1;
+    p.win_rot_c = std::cos(2.0 * kPi * 64.0 / t.win_len); p.win_rot_s = std::sin(2.0 * kPi * 64.0 / t.win_len);
     p.out = nullptr;
     p.rows_out = (int)(patches * 96);
     p.frames_valid = p.rows_out;
@@ -823,6 +851,7 @@ int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int6
     p.tw = t.tw; p.win = t.win;
     p.band_start = t.band_start; p.band_len = t.band_len;
     p.band_wt = t.band_wt; p.wt_rows = t.wt_rows; p.wt_off1 = t.wt_off1;
+    p.win_rot_c = std::cos(2.0 * kPi * 64.0 / t.win_len); p.win_rot_s = std::sin(2.0 * kPi * 64.0 / t.win_len);
     p.out = feats;
     if (model == FADB_MODEL_VGGISH) {
         const int64_t patches = frontend_rows(model, n_samples);

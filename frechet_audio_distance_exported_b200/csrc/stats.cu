@@ -20,9 +20,18 @@ __global__ void __launch_bounds__(256) stats_colsum_kernel(const TIn* __restrict
     if (r1 > n) r1 = n;
     if (c < d && r0 < r1) {
         const double k = shift ? shift[c] : 0.0;
-        double s = 0.0;
-        for (long long r = r0; r < r1; ++r) s += (double)__ldg(x + r * ld + c) - k;
-        atomicAdd(acc + 1 + c, s);
+        // four independent chains: the loop is a latency chain of dependent loads + adds otherwise (ncu r02: 107 us for
+        // 4000 x 128 floats = 19 GB/s with one chain and 1024 rows per CTA)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        long long r = r0;
+        for (; r + 3 < r1; r += 4) {
+            s0 += (double)__ldg(x + r * ld + c) - k;
+            s1 += (double)__ldg(x + (r + 1) * ld + c) - k;
+            s2 += (double)__ldg(x + (r + 2) * ld + c) - k;
+            s3 += (double)__ldg(x + (r + 3) * ld + c) - k;
+        }
+        for (; r < r1; ++r) s0 += (double)__ldg(x + r * ld + c) - k;
+        atomicAdd(acc + 1 + c, (s0 + s1) + (s2 + s3));
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(acc, (double)n);
 }
@@ -133,7 +142,7 @@ static int stats_accumulate_t(fadb_handle* h, const TIn* emb, int64_t n, int d, 
     FADB_REQUIRE(ld >= d, "row stride %lld < d", (long long)ld);
     if (n <= 0) return FADB_OK;
     {
-        int rows_per = 1024;
+        int rows_per = 128;
         long long ny = (n + rows_per - 1) / rows_per;
         while (ny > 32768) { rows_per *= 2; ny = (n + rows_per - 1) / rows_per; }
         dim3 grid((d + 255) / 256, (unsigned)ny);
