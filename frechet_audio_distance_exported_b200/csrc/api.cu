@@ -479,6 +479,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_PAIR_HALO")) h->gemm_pair_halo = atoi(e);
     if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
+    if (const char* e = getenv("FADB_TC_SYRK")) h->tc_syrk = atoi(e);
     if (const char* e = getenv("FADB_X2_MASK")) h->x2_mask = (unsigned)strtoul(e, nullptr, 0);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
@@ -496,6 +497,7 @@ void fadb_destroy(fadb_handle* h) {
     frontend_release(h);
     h->weight_pool.release();
     h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
+    h->ws_syrk.release();
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->ws_a1[0].release();

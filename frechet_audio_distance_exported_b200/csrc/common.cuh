@@ -145,6 +145,8 @@ struct fadb_handle {
     fadb::DevBuf ws_misc;       // pooled vectors etc.
     fadb::DevBuf ws_frechet;    // fp64 workspace of fadb_frechet
     fadb::DevBuf ws_stats;      // fp64 workspace of fadb_fad_from_pcm_host
+    fadb::DevBuf ws_syrk;       // tensor-core syrk: transposed split-fp16 planes of one row chunk + its fp32 product
+    int tc_syrk = 1;            // d >= 512: second moments on the tensor cores (FADB_TC_SYRK=0: always the fp64 DFMA kernel)
     fadb::DevBuf ws_pcm[2];     // double-buffered PCM chunks for the host path
     fadb::DevBuf ws_emb;        // embeddings of the host path
     // optional per-launch timing of the tensor-core layers (bench.py roofline leg)
@@ -201,6 +203,10 @@ struct LayerIO {
     __nv_bfloat16* out_lo = nullptr;           // may be null
     float* out_f32 = nullptr;                  // if set, fp32 output instead of bf16
     int use_lo_weights = 1;                    // fp16x2: 0 = this layer runs single-pass (FADB_X2_MASK sensitivity sweeps)
+    // statistics (stats.cu): C = Y Y^T as a "linear layer" whose activations and weights are the same split-fp16 matrix —
+    // fp16 hi/lo planes on both sides, 3 MMAs per product, N tiles of 128, tiles strictly below the diagonal skipped.
+    // Overrides the handle's precision for this launch.
+    int syrk = 0;
 };
 int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, cudaStream_t st);
 int gemm_init(fadb_handle* h);

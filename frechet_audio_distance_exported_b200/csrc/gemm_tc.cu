@@ -65,6 +65,7 @@ struct GemmParams {
                           // round-to-nearest.  The fp32 accumulation inside tcgen05.mma truncates, a bias that grows with
                           // the chain length (5e-6 of the output at K = 4608) and shrinks every activation of every
                           // layer the same way: cutting the chains to <= 64 MMAs removes it (FAD: 2e-4 -> 1e-5).
+    int upper_only;       // syrk: work units whose N tile lies strictly below the diagonal of their M rows are skipped
     int halo;             // 1 = halo mode: one activation tile per channel block feeds all 9 taps
     int b_stages;         // halo mode: depth of the separate B ring
     int resb;             // halo mode: 1 = all weights of the (single) N tile stay resident in smem
@@ -193,6 +194,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         n0 = (unit - q * p.tiles_n) * BN;
         m = (q << cshift) + crank;
     };
+    // syrk (C = Y Y^T, linear-layer tiling: M tile = 128 rows): every role skips the same units, so the pipeline state
+    // (stages, accumulator segments) stays in step
+    auto skip_unit = [&](int unit) {
+        if (!p.upper_only) return false;
+        const int q = unit / p.tiles_n;
+        const int nt = unit - q * p.tiles_n;
+        return (nt + 1) * BN <= (q << cshift) * kTileM;
+    };
 
     const int kb_per_pass = p.taps * p.cin_blocks;
     // which activation / weight plane a pass multiplies: npass 1: (0,0); 2: (0,0),(0,1); 3: (0,0),(1,0),(0,1)
@@ -243,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 __syncwarp();
             }
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                if (skip_unit(unit)) continue;
                 int m, n0;
                 unit_tile(unit, m, n0);
                 const int wt = m % p.tiles_w; m /= p.tiles_w;
@@ -263,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                if (skip_unit(unit)) continue;
                 int m, n0;
                 unit_tile(unit, m, n0);
                 const int wt = m % p.tiles_w; m /= p.tiles_w;
@@ -322,6 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int bs = 0;
             uint32_t bphase = 0;
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                if (skip_unit(unit)) continue;
                 int m, n0;
                 unit_tile(unit, m, n0);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
@@ -351,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             tc_fence_after();
         }
         for (int unit = unit0; issuer && unit < p.num_units; unit += ustep) {
+            if (skip_unit(unit)) continue;
             uint32_t tmem_d = 0;
             int seg_left = 0, as = 0;                           // channel blocks left in the open segment
             // The per-tap work is kept to a handful of uniform instructions: all 9 tap views are constant offsets
@@ -427,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             uint32_t phase = 0;
             int gs = 0;
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                if (skip_unit(unit)) continue;
                 for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
                     const int as = gs & 1;
                     const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
@@ -462,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             uint32_t phase = 0;
             int gs = 0;
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
+                if (skip_unit(unit)) continue;
                 for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
                     const int as = gs & 1;
                     const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
@@ -514,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         constexpr int NC = BN / 64;                  // 32-column chunks per thread: chunk index c = grp + 2 * ci
         int gs = 0;                                  // running segment count (same sequence as the MMA warp's)
         for (int unit = unit0; unit < p.num_units; unit += ustep) {
+            if (skip_unit(unit)) continue;
             int m, n0;
             unit_tile(unit, m, n0);
             const int wt = m % p.tiles_w; m /= p.tiles_w;
@@ -744,13 +760,16 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     FADB_REQUIRE(io.Cin == L.Cin && io.taps == L.taps, "layer/IO mismatch (Cin %d vs %d, taps %d vs %d)", io.Cin,
                  L.Cin, io.taps, L.taps);
     FADB_REQUIRE(io.taps == 9 || io.taps == 1, "taps must be 1 or 9");
-    const bool f16 = prec_is_f16(h->precision);
+    const bool f16 = io.syrk ? true : prec_is_f16(h->precision);
     FADB_REQUIRE(L.f16 == (int)f16, "layer weights were packed for %s but the handle's precision wants %s: commit the weights "
                  "again after fadb_set_precision", L.f16 ? "fp16" : "bf16", f16 ? "fp16" : "bf16");
     // operand passes over K (see GemmParams::npass)
-    const int npass = (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3
+    const int npass = io.syrk ? 3
+                      : (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3
                       : (h->precision == FADB_PREC_FP16X2 && L.w_lo && io.use_lo_weights) ? 2 : 1;
-    const int BN = (L.N % 256 == 0) ? 256 : (L.N % 128 == 0 ? 128 : 64);
+    const int BN = (L.N % 256 == 0 && !io.syrk) ? 256 : (L.N % 128 == 0 ? 128 : 64);
+    if (io.syrk) FADB_REQUIRE(io.in_lo && L.w_lo && io.taps == 1 && io.H == 1 && io.B == 1 && io.out_f32 && BN == 128,
+                              "syrk launch: needs both lo planes, linear-layer shape, fp32 output and N %% 128 == 0");
     FADB_REQUIRE(L.N % BN == 0 && L.N >= 64, "Cout=%d must be a multiple of 64", L.N);
     FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
 
@@ -824,7 +843,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.Wo = io.pool ? io.W / 2 : io.W;
     p.bias = L.bias;
     p.out_hi = io.out_hi;
-    p.out_lo = (h->precision == FADB_PREC_BF16X3) ? io.out_lo : nullptr;
+    p.out_lo = (h->precision == FADB_PREC_BF16X3 && !io.syrk) ? io.out_lo : nullptr;
+    p.upper_only = io.syrk;
     p.out_f32 = io.out_f32;
     p.err_flag = h->err_flag;
     FADB_REQUIRE(p.out_f32 || p.out_hi, "layer has no output buffer");

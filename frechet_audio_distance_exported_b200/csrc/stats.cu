@@ -5,6 +5,8 @@
 // so partials from batches / GPUs add (NCCL allreduce between accumulate and finalize).
 // The d x d second moment is an fp64 DFMA syrk over 128x128 upper-triangular tiles, rows split across
 // CTAs, one fp64 atomicAdd flush per CTA tile.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fadb {
@@ -119,6 +121,92 @@ __global__ void __launch_bounds__(256, 1) stats_syrk_kernel(const TIn* __restric
         }
 }
 
+// ---------------------------------------------------------------- syrk on the tensor cores (d >= 512)
+// S += Y^T Y with Y = X - K as ONE launch of the tcgen05 implicit-GEMM kernel per chunk of <= 65536 rows: the
+// "activations" and the "weights" of that linear layer are the same matrix Yt = Y^T [d][rows] (K-major for both MMA
+// operands), split into IEEE fp16 hi + lo planes (y = hi + lo to 2^-22), three MMAs per product (hi hi, lo hi, hi lo;
+// lo lo ~ 2^-24 is dropped), each pass its own accumulation segments, segment sums added in fp32 round-to-nearest by
+// the epilogue (gemm_tc.cu).  Tiles strictly below the diagonal are skipped.  The chunk's fp32 product is then added
+// to the fp64 statistic.  Replaces 2 N d^2 fp64 DFMA flops by 3 x N d^2 tensor flops: 634 ms -> ~30 ms for two sets of
+// 1e6 x 2048 (BASELINE configs[4]); the fp64 kernel above stays for d < 512 and as the checker.
+constexpr int kSyrkChunkRows = 65536;
+
+// x [n][ld] (rows r0 ..) -> hi / lo [d][kpad] fp16, zero beyond the chunk's rows; 32 x 32 tiles through shared memory
+template <typename TIn>
+__global__ void __launch_bounds__(256) syrk_split_transpose_kernel(const TIn* __restrict__ x, long long rows, int d,
+                                                                   long long ld, const double* __restrict__ shift,
+                                                                   int kpad, __half* __restrict__ hi,
+                                                                   __half* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32;                 // feature block
+    const long long r0 = (long long)blockIdx.y * 32;      // row block (within the chunk)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + ty + 8 * i;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (r < rows && c < d) v = (float)((double)__ldg(x + r * ld + c) - (shift ? shift[c] : 0.0));
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i;              // feature = output row
+        const long long r = r0 + tx;                // sample = output column
+        if (c < d && r < kpad) {
+            const float v = fminf(fmaxf(tile[tx][ty + 8 * i], -65504.f), 65504.f);
+            const __half h = __float2half_rn(v);
+            hi[(size_t)c * kpad + r] = h;
+            lo[(size_t)c * kpad + r] = __float2half_rn(v - __half2float(h));
+        }
+    }
+}
+
+// S (fp64, upper 128 x 128 tiles) += C (fp32 product of one chunk)
+__global__ void syrk_add_kernel(const float* __restrict__ C, int d, double* __restrict__ S) {
+    const size_t total = (size_t)d * d;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / d), j = (int)(e % d);
+        if (i / TS <= j / TS) S[e] += (double)C[e];
+    }
+}
+
+static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d, int64_t ld, const double* shift,
+                             double* S, cudaStream_t st) {
+    const int64_t chunk = n < kSyrkChunkRows ? ((n + 63) / 64) * 64 : kSyrkChunkRows;
+    const size_t plane = (size_t)d * chunk;                                   // fp16 elements per plane
+    const size_t bytes = 2 * plane * sizeof(__half) + (size_t)d * d * sizeof(float) + 256;
+    FADB_CHECK(h->ws_syrk.reserve(bytes));
+    __half* hi = h->ws_syrk.as<__half>();
+    __half* lo = hi + plane;
+    float* C = reinterpret_cast<float*>(lo + plane);
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
+        const int kpad = (int)(((rows + 63) / 64) * 64);
+        dim3 grid((d + 31) / 32, (unsigned)(kpad / 32));
+        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, shift, kpad, hi, lo);
+        PackedLayer L;
+        L.N = d; L.K = kpad; L.Cin = kpad; L.taps = 1; L.f16 = 1;
+        L.w_hi = reinterpret_cast<__nv_bfloat16*>(hi);
+        L.w_lo = reinterpret_cast<__nv_bfloat16*>(lo);
+        L.bias = nullptr;
+        LayerIO io;
+        io.in_hi = reinterpret_cast<const __nv_bfloat16*>(hi);
+        io.in_lo = reinterpret_cast<const __nv_bfloat16*>(lo);
+        io.B = 1; io.H = 1; io.W = d; io.Cin = kpad; io.taps = 1; io.relu = 0; io.pool = 0;
+        io.out_f32 = C;
+        io.syrk = 1;
+        FADB_CHECK(launch_gemm_layer(h, L, io, st));
+        int g = (int)(((size_t)d * d + 255) / 256);
+        if (g > 148 * 16) g = 148 * 16;
+        syrk_add_kernel<<<g, 256, 0, st>>>(C, d, S);
+        h->launches += 2;
+    }
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
 // ---------------------------------------------------------------- finalize
 __global__ void stats_finalize_kernel(const double* __restrict__ acc, int d, const double* __restrict__ shift,
                                       double* __restrict__ mu, double* __restrict__ sigma) {
@@ -149,7 +237,10 @@ static int stats_accumulate_t(fadb_handle* h, const TIn* emb, int64_t n, int d, 
         stats_colsum_kernel<TIn><<<grid, 256, 0, st>>>(emb, n, d, ld, shift, acc, rows_per);
         h->launches++;
     }
-    {
+    if (std::is_same<TIn, float>::value && h->tc_syrk && d >= 512 && d % 128 == 0 && n >= 1024) {
+        // second moments on the tensor cores (the packed linear-layer path needs d % 128 == 0)
+        FADB_CHECK(stats_syrk_tensor(h, reinterpret_cast<const float*>(emb), n, d, ld, shift, acc + 1 + d, st));
+    } else {
         const int ntile = (d + TS - 1) / TS;
         const int npair = ntile * (ntile + 1) / 2;
         long long want = (2LL * h->sm_count + npair - 1) / npair;           // row splits to fill the machine

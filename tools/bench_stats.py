@@ -11,7 +11,10 @@ from frechet_audio_distance_exported_b200.engine import Engine
 from oracle import networks, stats
 
 cpu = "--no-cpu" not in sys.argv
-eng = Engine("vggish", networks.vggish_random_state_dict(0))
+eng = Engine("vggish")
+os.environ["FADB_TC_SYRK"] = "0"
+eng64 = Engine("vggish")                                 # the fp64 DFMA syrk as the checker of the tensor-core path
+os.environ.pop("FADB_TC_SYRK")
 dev = eng.device
 
 
@@ -49,9 +52,22 @@ for d in (128, 512, 2048):
             return out
         ms_stats, ((mu1, s1), (mu2, s2)) = gpu_ms(stats_both)
         ms_fr, fr = gpu_ms(lambda: eng.frechet(mu1, s1, mu2, s2))
+
+        def stats_both64():
+            out = []
+            for x in (x1, x2):
+                acc = eng64.new_acc(d)
+                eng64.stats_accumulate(x, acc)
+                out.append(eng64.stats_finalize(acc, d))
+            return out
+        ms64, ((m1_, c1_), (m2_, c2_)) = gpu_ms(stats_both64, reps=1)
+        fr64 = eng64.frechet(m1_, c1_, m2_, c2_)
+        tc_vs_64 = {"fp64_kernel_stats_ms_both_sets": ms64,
+                    "sigma_rel_err_vs_fp64_kernel": float((s1 - c1_).abs().max() / c1_.abs().max()),
+                    "fad_rel_err_vs_fp64_kernel": abs(float(fr[0]) - float(fr64[0])) / abs(float(fr64[0]))}
         rec = {"d": d, "n_per_set": n, "gpu_stats_ms_both_sets": ms_stats, "gpu_frechet_ms": ms_fr, "fad": float(fr[0]),
                "stats_rows_per_s": 2 * n / ms_stats * 1e3, "stats_read_gbs": 2 * n * d * 4 / ms_stats / 1e6,
-               "stats_fp64_tflops": 2 * n * d * (d + 1) / ms_stats / 1e9}
+               "stats_tflops": 2 * n * d * (d + 1) / ms_stats / 1e9, **tc_vs_64}
         if cpu and n <= 100_000:
             h1, h2 = x1.cpu().numpy(), x2.cpu().numpy()
             t0 = time.perf_counter()
