@@ -207,6 +207,7 @@ struct LayerIO {
     // fp16 hi/lo planes on both sides, 3 MMAs per product, N tiles of 128, tiles strictly below the diagonal skipped.
     // Overrides the handle's precision for this launch.
     int syrk = 0;
+    int seg_blocks = 0;                        // K blocks per accumulation segment (0 = the default 16 = 64 MMAs)
 };
 int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, cudaStream_t st);
 int gemm_init(fadb_handle* h);

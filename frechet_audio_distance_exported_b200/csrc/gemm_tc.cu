@@ -993,7 +993,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         p.seg_len = kSegmentBlocks / (9 * npass) > 0 ? kSegmentBlocks / (9 * npass) : 1;
         p.nseg = (p.cin_blocks + p.seg_len - 1) / p.seg_len;
     } else {
-        p.nseg = (p.nkb + kSegmentBlocks - 1) / kSegmentBlocks;
+        const int kseg = io.seg_blocks > 0 ? io.seg_blocks : kSegmentBlocks;
+        p.nseg = (p.nkb + kseg - 1) / kseg;
         p.seg_len = (p.nkb + p.nseg - 1) / p.nseg;
         p.nseg = (p.nkb + p.seg_len - 1) / p.seg_len;
     }

@@ -131,44 +131,64 @@ __global__ void __launch_bounds__(256, 1) stats_syrk_kernel(const TIn* __restric
 // 1e6 x 2048 (BASELINE configs[4]); the fp64 kernel above stays for d < 512 and as the checker.
 constexpr int kSyrkChunkRows = 65536;
 
-// x [n][ld] (rows r0 ..) -> hi / lo [d][kpad] fp16, zero beyond the chunk's rows; 32 x 32 tiles through shared memory
+// x [rows][ld] -> hi / lo [d][kpad] fp16 of y = x - K', K' = the chunk's own column mean (csum[1 + c] / rows, fp64), zero
+// beyond the chunk's rows.  Centring on the chunk mean keeps the products free of the mean^2 term (the fp32 chains
+// inside the MMA truncate: a bias relative to the SECOND MOMENT, which the subtraction of mu mu^T would amplify).
+// 64 features x 64 samples per CTA through shared memory; every thread writes 16 consecutive samples of one feature
+// (two 16-byte stores per plane), a warp covers 8 complete 128-byte rows.
 template <typename TIn>
 __global__ void __launch_bounds__(256) syrk_split_transpose_kernel(const TIn* __restrict__ x, long long rows, int d,
-                                                                   long long ld, const double* __restrict__ shift,
+                                                                   long long ld, const double* __restrict__ csum,
                                                                    int kpad, __half* __restrict__ hi,
                                                                    __half* __restrict__ lo) {
-    __shared__ float tile[32][33];
-    const int c0 = blockIdx.x * 32;                 // feature block
-    const long long r0 = (long long)blockIdx.y * 32;      // row block (within the chunk)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long r = r0 + ty + 8 * i;
-        const int c = c0 + tx;
-        float v = 0.f;
-        if (r < rows && c < d) v = (float)((double)__ldg(x + r * ld + c) - (shift ? shift[c] : 0.0));
-        tile[ty + 8 * i][tx] = v;
+    __shared__ float tile[64][65];                          // [sample][feature]
+    const int c0 = blockIdx.x * 64;
+    const long long r0 = (long long)blockIdx.y * 64;
+    {
+        const int f = threadIdx.x & 63, c = c0 + f;
+        const double kp = (c < d) ? csum[1 + c] / (double)rows : 0.0;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int sl = (threadIdx.x >> 6) + 4 * i;
+            const long long r = r0 + sl;
+            float v = 0.f;
+            if (r < rows && c < d) v = (float)((double)__ldg(x + r * ld + c) - kp);
+            tile[sl][f] = v;
+        }
     }
     __syncthreads();
+    const int f = threadIdx.x >> 2, part = threadIdx.x & 3, c = c0 + f;
+    if (c < d && r0 + 16 * part < kpad) {
+        uint32_t ph[8], pl[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i;              // feature = output row
-        const long long r = r0 + tx;                // sample = output column
-        if (c < d && r < kpad) {
-            const float v = fminf(fmaxf(tile[tx][ty + 8 * i], -65504.f), 65504.f);
-            const __half h = __float2half_rn(v);
-            hi[(size_t)c * kpad + r] = h;
-            lo[(size_t)c * kpad + r] = __float2half_rn(v - __half2float(h));
+        for (int k = 0; k < 8; ++k) {
+            const float v0 = fminf(fmaxf(tile[16 * part + 2 * k][f], -65504.f), 65504.f);
+            const float v1 = fminf(fmaxf(tile[16 * part + 2 * k + 1][f], -65504.f), 65504.f);
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const __half2 l = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
+            ph[k] = *reinterpret_cast<const uint32_t*>(&h);
+            pl[k] = *reinterpret_cast<const uint32_t*>(&l);
         }
+        uint4* dh = reinterpret_cast<uint4*>(hi + (size_t)c * kpad + r0 + 16 * part);
+        uint4* dl = reinterpret_cast<uint4*>(lo + (size_t)c * kpad + r0 + 16 * part);
+        dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
     }
 }
 
-// S (fp64, upper 128 x 128 tiles) += C (fp32 product of one chunk)
-__global__ void syrk_add_kernel(const float* __restrict__ C, int d, double* __restrict__ S) {
+// S (fp64, upper 128 x 128 tiles) += C (fp32 centred product of one chunk) + rows * delta delta^T,
+// delta = K' - K (chunk mean minus the caller's common shift): sum (x-K)(x-K)^T = sum y y^T + rows delta delta^T
+// because sum y = 0 for y = x - K'.
+__global__ void syrk_add_kernel(const float* __restrict__ C, int d, const double* __restrict__ csum, long long rows,
+                                const double* __restrict__ shift, double* __restrict__ S) {
     const size_t total = (size_t)d * d;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / d), j = (int)(e % d);
-        if (i / TS <= j / TS) S[e] += (double)C[e];
+        if (i / TS <= j / TS) {
+            const double di = csum[1 + i] / (double)rows - (shift ? shift[i] : 0.0);
+            const double dj = csum[1 + j] / (double)rows - (shift ? shift[j] : 0.0);
+            S[e] += (double)C[e] + (double)rows * di * dj;
+        }
     }
 }
 
@@ -176,16 +196,25 @@ static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d,
                              double* S, cudaStream_t st) {
     const int64_t chunk = n < kSyrkChunkRows ? ((n + 63) / 64) * 64 : kSyrkChunkRows;
     const size_t plane = (size_t)d * chunk;                                   // fp16 elements per plane
-    const size_t bytes = 2 * plane * sizeof(__half) + (size_t)d * d * sizeof(float) + 256;
+    const size_t csum_bytes = ((size_t)(1 + d) * sizeof(double) + 255) / 256 * 256;
+    const size_t bytes = 2 * plane * sizeof(__half) + (size_t)d * d * sizeof(float) + csum_bytes + 256;
     FADB_CHECK(h->ws_syrk.reserve(bytes));
     __half* hi = h->ws_syrk.as<__half>();
     __half* lo = hi + plane;
     float* C = reinterpret_cast<float*>(lo + plane);
+    double* csum = reinterpret_cast<double*>(reinterpret_cast<char*>(C) + (((size_t)d * d * sizeof(float) + 255) / 256 * 256));
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         const int kpad = (int)(((rows + 63) / 64) * 64);
-        dim3 grid((d + 31) / 32, (unsigned)(kpad / 32));
-        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, shift, kpad, hi, lo);
+        // chunk column sums (fp64) -> the chunk's own centre K'
+        FADB_CUDA_CHECK(cudaMemsetAsync(csum, 0, (size_t)(1 + d) * sizeof(double), st));
+        {
+            const int rows_per = 256;
+            dim3 g((d + 255) / 256, (unsigned)((rows + rows_per - 1) / rows_per));
+            stats_colsum_kernel<float><<<g, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, nullptr, csum, rows_per);
+        }
+        dim3 grid((d + 63) / 64, (unsigned)(kpad / 64));
+        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, csum, kpad, hi, lo);
         PackedLayer L;
         L.N = d; L.K = kpad; L.Cin = kpad; L.taps = 1; L.f16 = 1;
         L.w_hi = reinterpret_cast<__nv_bfloat16*>(hi);
@@ -197,11 +226,12 @@ static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d,
         io.B = 1; io.H = 1; io.W = d; io.Cin = kpad; io.taps = 1; io.relu = 0; io.pool = 0;
         io.out_f32 = C;
         io.syrk = 1;
+        io.seg_blocks = 4;              // 16-MMA chains: truncation bias ~3e-7 of the centred second moment
         FADB_CHECK(launch_gemm_layer(h, L, io, st));
         int g = (int)(((size_t)d * d + 255) / 256);
         if (g > 148 * 16) g = 148 * 16;
-        syrk_add_kernel<<<g, 256, 0, st>>>(C, d, S);
-        h->launches += 2;
+        syrk_add_kernel<<<g, 256, 0, st>>>(C, d, csum, rows, shift, S);
+        h->launches += 3;
     }
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
