@@ -208,6 +208,9 @@ struct LayerIO {
     // Overrides the handle's precision for this launch.
     int syrk = 0;
     int seg_blocks = 0;                        // K blocks per accumulation segment (0 = the default 16 = 64 MMAs)
+    double* out_f64 = nullptr;                 // syrk: fp64 matrix the finished tiles are ADDED to
+    long long row_stride = 0;                  // linear layers: elements between rows of the activation AND weight
+                                               // matrices (0 = dense); lets a caller avoid power-of-two strides
 };
 int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, cudaStream_t st);
 int gemm_init(fadb_handle* h);

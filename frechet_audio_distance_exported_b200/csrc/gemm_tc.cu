@@ -30,6 +30,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -76,6 +77,7 @@ struct GemmParams {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     float* out_f32;
+    double* out_f64;      // syrk: the fp64 statistic itself; the epilogue ADDS the tile (read-modify-write, one owner per tile)
     int* err_flag;
 };
 
@@ -110,7 +112,9 @@ struct GemmCfg {
 // cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
 // F16 = activations and weights are IEEE fp16 instead of bf16 (same kind::f16 MMA at the same rate; 8x smaller operand
 // rounding error, range +-65504 with saturation in the epilogue).
-template <int BN, bool PAIR, bool F16>
+// SYRK = the statistics variant (stats.cu): segment sums are added in fp64 registers and the finished tile is added to the
+// fp64 second-moment matrix; no bias / activation / pooling.
+template <int BN, bool PAIR, bool F16, bool SYRK = false>
 __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     const int kStages = p.stages;
@@ -550,11 +554,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             // ---- add the tile's accumulation segments in fp32 registers (round-to-nearest): run[ci][j] = this row's
             // column n0 + 32 * (grp + 2 ci) + j.  A segment's accumulator goes back to the MMA warp as soon as it has
             // been read, so the tensor pipe runs the next segment while this one is being added.
-            float run[NC][32];
+            using run_t = typename std::conditional<SYRK, double, float>::type;
+            run_t run[NC][32];
 #pragma unroll
             for (int ci = 0; ci < NC; ++ci)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) run[ci][j] = 0.f;
+                for (int j = 0; j < 32; ++j) run[ci][j] = 0;
 #pragma unroll 1
             for (int seg = 0; seg < p.nseg; ++seg, ++gs) {
                 const int as = gs & 1;
@@ -567,7 +572,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     tmem_ld_32x32b_x32(taddr + ci * 64, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) {
+                        if constexpr (SYRK) run[ci][j] += (double)__uint_as_float(r[j]);
+                        else run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -577,10 +585,28 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 }
             }
 
+            if constexpr (SYRK) {
+                // S[row][n0 + 32 c + j] += tile sum, for tiles on or above the diagonal (128-granular, like stats_finalize
+                // reads them); every (M tile, N tile) has exactly one owner in a launch, launches are stream-ordered
+                const bool keep = valid && (n0 / kTileM >= x / kTileM);
+#pragma unroll
+                for (int ci = 0; ci < NC; ++ci) {
+                    double2* dst = reinterpret_cast<double2*>(p.out_f64 + obase + (grp + 2 * ci) * 32);
+                    if (keep) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            double2 t = dst[j];
+                            t.x += run[ci][2 * j];
+                            t.y += run[ci][2 * j + 1];
+                            dst[j] = t;
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int ci = 0; ci < NC; ++ci) {
                 const int c = grp + 2 * ci;
-                float (&v)[32] = run[ci];
+                float (&v)[32] = reinterpret_cast<float (&)[32]>(run[ci]);
                 {
                     const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c * 32);
 #pragma unroll
@@ -676,6 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     }
                 }
             }
+            }   // !SYRK
         }
     }
 
@@ -716,14 +743,18 @@ int gemm_init(fadb_handle* h) {
                                   fadb_gemm_tc_kernel<128, true, false>, fadb_gemm_tc_kernel<256, true, false>,
                                   fadb_gemm_tc_kernel<64, false, true>, fadb_gemm_tc_kernel<128, false, true>,
                                   fadb_gemm_tc_kernel<256, false, true>, fadb_gemm_tc_kernel<64, true, true>,
-                                  fadb_gemm_tc_kernel<128, true, true>, fadb_gemm_tc_kernel<256, true, true>})
+                                  fadb_gemm_tc_kernel<128, true, true>, fadb_gemm_tc_kernel<256, true, true>,
+                                  fadb_gemm_tc_kernel<128, false, true, true>, fadb_gemm_tc_kernel<128, true, true, true>})
         FADB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kMaxSmemBytes));
     return FADB_OK;
 }
 
-static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB, bool f16) {
+// rs = row stride in elements (0 = C: rows are dense)
+static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB, bool f16,
+                          long long rs = 0) {
+    if (rs <= 0) rs = C;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)W * rs * 2, (cuuint64_t)H * W * rs * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
@@ -738,9 +769,10 @@ static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H,
     return FADB_OK;
 }
 
-static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN, bool f16) {
+static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN, bool f16, long long rs = 0) {
+    if (rs <= 0) rs = K;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)rs * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -768,8 +800,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                       : (h->precision == FADB_PREC_BF16X3 && io.in_lo && L.w_lo) ? 3
                       : (h->precision == FADB_PREC_FP16X2 && L.w_lo && io.use_lo_weights) ? 2 : 1;
     const int BN = (L.N % 256 == 0 && !io.syrk) ? 256 : (L.N % 128 == 0 ? 128 : 64);
-    if (io.syrk) FADB_REQUIRE(io.in_lo && L.w_lo && io.taps == 1 && io.H == 1 && io.B == 1 && io.out_f32 && BN == 128,
-                              "syrk launch: needs both lo planes, linear-layer shape, fp32 output and N %% 128 == 0");
+    if (io.syrk) FADB_REQUIRE(io.in_lo && L.w_lo && io.taps == 1 && io.H == 1 && io.B == 1 && io.out_f64 && BN == 128,
+                              "syrk launch: needs both lo planes, linear-layer shape, fp64 output and N %% 128 == 0");
     FADB_REQUIRE(L.N % BN == 0 && L.N >= 64, "Cout=%d must be a multiple of 64", L.N);
     FADB_REQUIRE(io.B > 0 && io.H > 0 && io.W > 0, "empty layer input");
 
@@ -815,15 +847,15 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16));
+    FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16, io.row_stride));
     if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1, f16));
     else p.tmH = p.tmA[0];
     p.halo = halo;
-    FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN, f16));
+    FADB_CHECK(encode_weight_map(&p.tmB[0], L.w_hi, L.K, L.N, BN, f16, io.row_stride));
     p.tmA[1] = p.tmA[0];
     p.tmB[1] = p.tmB[0];
-    if (npass == 3) FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16));
-    if (npass >= 2) FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN, f16));
+    if (npass == 3) FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16, io.row_stride));
+    if (npass >= 2) FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN, f16, io.row_stride));
     p.W = io.W; p.H = io.H; p.B = io.B;
     p.BW = BW; p.BH = BH; p.BB = BB;
     p.tiles_w = (io.W + BW - 1) / BW;
@@ -846,8 +878,9 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.out_lo = (h->precision == FADB_PREC_BF16X3 && !io.syrk) ? io.out_lo : nullptr;
     p.upper_only = io.syrk;
     p.out_f32 = io.out_f32;
+    p.out_f64 = io.out_f64;
     p.err_flag = h->err_flag;
-    FADB_REQUIRE(p.out_f32 || p.out_hi, "layer has no output buffer");
+    FADB_REQUIRE(p.out_f32 || p.out_hi || p.out_f64, "layer has no output buffer");
 
     const int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -915,8 +948,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             pp.num_units = pair_units;
             if (pair_mode) { pp.twocta = 1; apply(pair); smem = pair.smem; }
             g = cs * (h->sm_count / cs);
-            if (encode_weight_map(&pp.tmBh[0], L.w_hi, L.K, L.N, BN / cs, f16) != FADB_OK ||
-                (npass >= 2 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16) != FADB_OK)) {
+            if (encode_weight_map(&pp.tmBh[0], L.w_hi, L.K, L.N, BN / cs, f16, io.row_stride) != FADB_OK ||
+                (npass >= 2 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16, io.row_stride) != FADB_OK)) {
                 pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; pp.twocta = 0; apply(plain); smem = plain.smem;
             }
             if (npass < 2) pp.tmBh[1] = pp.tmBh[0];
@@ -933,6 +966,10 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
                                : (BN == 128 ? fadb_gemm_tc_kernel<128, false, false> : fadb_gemm_tc_kernel<64, false, false>);
             kern_pair = (BN == 256) ? fadb_gemm_tc_kernel<256, true, false>
                                     : (BN == 128 ? fadb_gemm_tc_kernel<128, true, false> : fadb_gemm_tc_kernel<64, true, false>);
+        }
+        if (io.syrk) {
+            kern = fadb_gemm_tc_kernel<128, false, true, true>;
+            kern_pair = fadb_gemm_tc_kernel<128, true, true, true>;
         }
         void (*kern_plain)(GemmParams) = kern;
         if (pp.twocta) kern = kern_pair;

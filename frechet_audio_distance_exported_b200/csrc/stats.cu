@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256, 1) stats_syrk_kernel(const TIn* __restric
 // 1e6 x 2048 (BASELINE configs[4]); the fp64 kernel above stays for d < 512 and as the checker.
 constexpr int kSyrkChunkRows = 65536;
 
-// x [rows][ld] -> hi / lo [d][kpad] fp16 of y = x - K', K' = the chunk's own column mean (csum[1 + c] / rows, fp64), zero
+// x [rows][ld] -> hi / lo [d][stride] fp16 (kpad <= stride columns written) of y = x - K', K' = the chunk's own column mean (csum[1 + c] / rows, fp64), zero
 // beyond the chunk's rows.  Centring on the chunk mean keeps the products free of the mean^2 term (the fp32 chains
 // inside the MMA truncate: a bias relative to the SECOND MOMENT, which the subtraction of mu mu^T would amplify).
 // 64 features x 64 samples per CTA through shared memory; every thread writes 16 consecutive samples of one feature
@@ -139,7 +139,7 @@ constexpr int kSyrkChunkRows = 65536;
 template <typename TIn>
 __global__ void __launch_bounds__(256) syrk_split_transpose_kernel(const TIn* __restrict__ x, long long rows, int d,
                                                                    long long ld, const double* __restrict__ csum,
-                                                                   int kpad, __half* __restrict__ hi,
+                                                                   int stride, int kpad, __half* __restrict__ hi,
                                                                    __half* __restrict__ lo) {
     __shared__ float tile[64][65];                          // [sample][feature]
     const int c0 = blockIdx.x * 64;
@@ -169,40 +169,45 @@ __global__ void __launch_bounds__(256) syrk_split_transpose_kernel(const TIn* __
             ph[k] = *reinterpret_cast<const uint32_t*>(&h);
             pl[k] = *reinterpret_cast<const uint32_t*>(&l);
         }
-        uint4* dh = reinterpret_cast<uint4*>(hi + (size_t)c * kpad + r0 + 16 * part);
-        uint4* dl = reinterpret_cast<uint4*>(lo + (size_t)c * kpad + r0 + 16 * part);
+        uint4* dh = reinterpret_cast<uint4*>(hi + (size_t)c * stride + r0 + 16 * part);
+        uint4* dl = reinterpret_cast<uint4*>(lo + (size_t)c * stride + r0 + 16 * part);
         dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
         dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
     }
 }
 
-// S (fp64, upper 128 x 128 tiles) += C (fp32 centred product of one chunk) + rows * delta delta^T,
-// delta = K' - K (chunk mean minus the caller's common shift): sum (x-K)(x-K)^T = sum y y^T + rows delta delta^T
-// because sum y = 0 for y = x - K'.
-__global__ void syrk_add_kernel(const float* __restrict__ C, int d, const double* __restrict__ csum, long long rows,
-                                const double* __restrict__ shift, double* __restrict__ S) {
+// S (fp64, upper 128 x 128 tiles) += rows * delta delta^T, delta = K' - K (chunk mean minus the caller's common shift):
+// sum (x-K)(x-K)^T = sum y y^T + rows delta delta^T because sum y = 0 for y = x - K'.  (sum y y^T is added by the GEMM's
+// own epilogue.)
+__global__ void syrk_rank1_kernel(int d, const double* __restrict__ csum, long long rows,
+                                  const double* __restrict__ shift, double* __restrict__ S) {
     const size_t total = (size_t)d * d;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / d), j = (int)(e % d);
         if (i / TS <= j / TS) {
             const double di = csum[1 + i] / (double)rows - (shift ? shift[i] : 0.0);
             const double dj = csum[1 + j] / (double)rows - (shift ? shift[j] : 0.0);
-            S[e] += (double)C[e] + (double)rows * di * dj;
+            S[e] += (double)rows * di * dj;
         }
     }
 }
 
 static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d, int64_t ld, const double* shift,
                              double* S, cudaStream_t st) {
-    const int64_t chunk = n < kSyrkChunkRows ? ((n + 63) / 64) * 64 : kSyrkChunkRows;
-    const size_t plane = (size_t)d * chunk;                                   // fp16 elements per plane
+    // Row chunks sized so that both fp16 planes of a chunk (4 d bytes per row) stay in L2 (126 MB) while every tile of
+    // the product re-reads them; the row stride gets 64 extra elements so that rows do not sit 2^k bytes apart.
+    int64_t chunk = (int64_t)(64u << 20) / (4 * (int64_t)d);
+    chunk = chunk / 64 * 64;
+    if (chunk > kSyrkChunkRows) chunk = kSyrkChunkRows;
+    if (chunk < 1024) chunk = 1024;
+    if (n < chunk) chunk = ((n + 63) / 64) * 64;
+    const int64_t stride = chunk + 64;
+    const size_t plane = (size_t)d * stride;                                  // fp16 elements per plane
     const size_t csum_bytes = ((size_t)(1 + d) * sizeof(double) + 255) / 256 * 256;
-    const size_t bytes = 2 * plane * sizeof(__half) + (size_t)d * d * sizeof(float) + csum_bytes + 256;
-    FADB_CHECK(h->ws_syrk.reserve(bytes));
-    __half* hi = h->ws_syrk.as<__half>();
+    FADB_CHECK(h->ws_syrk.reserve(2 * plane * sizeof(__half) + csum_bytes + 256));
+    double* csum = h->ws_syrk.as<double>();
+    __half* hi = reinterpret_cast<__half*>(h->ws_syrk.as<char>() + csum_bytes);
     __half* lo = hi + plane;
-    float* C = reinterpret_cast<float*>(lo + plane);
-    double* csum = reinterpret_cast<double*>(reinterpret_cast<char*>(C) + (((size_t)d * d * sizeof(float) + 255) / 256 * 256));
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         const int kpad = (int)(((rows + 63) / 64) * 64);
@@ -214,7 +219,7 @@ static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d,
             stats_colsum_kernel<float><<<g, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, nullptr, csum, rows_per);
         }
         dim3 grid((d + 63) / 64, (unsigned)(kpad / 64));
-        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, csum, kpad, hi, lo);
+        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, csum, (int)stride, kpad, hi, lo);
         PackedLayer L;
         L.N = d; L.K = kpad; L.Cin = kpad; L.taps = 1; L.f16 = 1;
         L.w_hi = reinterpret_cast<__nv_bfloat16*>(hi);
@@ -224,13 +229,14 @@ static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d,
         io.in_hi = reinterpret_cast<const __nv_bfloat16*>(hi);
         io.in_lo = reinterpret_cast<const __nv_bfloat16*>(lo);
         io.B = 1; io.H = 1; io.W = d; io.Cin = kpad; io.taps = 1; io.relu = 0; io.pool = 0;
-        io.out_f32 = C;
+        io.out_f64 = S;
+        io.row_stride = stride;
         io.syrk = 1;
         io.seg_blocks = 4;              // 16-MMA chains: truncation bias ~3e-7 of the centred second moment
         FADB_CHECK(launch_gemm_layer(h, L, io, st));
         int g = (int)(((size_t)d * d + 255) / 256);
         if (g > 148 * 16) g = 148 * 16;
-        syrk_add_kernel<<<g, 256, 0, st>>>(C, d, csum, rows, shift, S);
+        syrk_rank1_kernel<<<g, 256, 0, st>>>(d, csum, rows, shift, S);
         h->launches += 3;
     }
     FADB_CUDA_CHECK(cudaGetLastError());
