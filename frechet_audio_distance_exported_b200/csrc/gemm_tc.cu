@@ -591,15 +591,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 const bool keep = valid && (n0 / kTileM >= x / kTileM);
 #pragma unroll
                 for (int ci = 0; ci < NC; ++ci) {
-                    double2* dst = reinterpret_cast<double2*>(p.out_f64 + obase + (grp + 2 * ci) * 32);
+                    // (8-byte accesses: the statistic sits 1 + d doubles into the caller's buffer, so rows are not
+                    // 16-byte aligned in general)
+                    double* dst = p.out_f64 + obase + (grp + 2 * ci) * 32;
                     if (keep) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            double2 t = dst[j];
-                            t.x += run[ci][2 * j];
-                            t.y += run[ci][2 * j + 1];
-                            dst[j] = t;
-                        }
+                        for (int j = 0; j < 32; ++j) dst[j] += run[ci][j];
                     }
                 }
             } else {
