@@ -112,8 +112,9 @@ struct GemmCfg {
 // cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
 // F16 = activations and weights are IEEE fp16 instead of bf16 (same kind::f16 MMA at the same rate; 8x smaller operand
 // rounding error, range +-65504 with saturation in the epilogue).
-// SYRK = the statistics variant (stats.cu): segment sums are added in fp64 registers and the finished tile is added to the
-// fp64 second-moment matrix; no bias / activation / pooling.
+// SYRK = the statistics variant (stats.cu): the finished tile (fp32 segment sums of one short row chunk) is ADDED to the
+// fp64 second-moment matrix; no bias / activation / pooling.  (Adding every segment in fp64 registers was measured:
+// the 64 F2F conversions per thread and segment cost more than the MMAs of a 16-MMA segment.)
 template <int BN, bool PAIR, bool F16, bool SYRK = false>
 __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -554,8 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             // ---- add the tile's accumulation segments in fp32 registers (round-to-nearest): run[ci][j] = this row's
             // column n0 + 32 * (grp + 2 ci) + j.  A segment's accumulator goes back to the MMA warp as soon as it has
             // been read, so the tensor pipe runs the next segment while this one is being added.
-            using run_t = typename std::conditional<SYRK, double, float>::type;
-            run_t run[NC][32];
+            float run[NC][32];
 #pragma unroll
             for (int ci = 0; ci < NC; ++ci)
 #pragma unroll
@@ -572,10 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     tmem_ld_32x32b_x32(taddr + ci * 64, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if constexpr (SYRK) run[ci][j] += (double)__uint_as_float(r[j]);
-                        else run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
-                    }
+                    for (int j = 0; j < 32; ++j) run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -596,14 +593,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     double* dst = p.out_f64 + obase + (grp + 2 * ci) * 32;
                     if (keep) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[j] += run[ci][j];
+                        for (int j = 0; j < 32; ++j) dst[j] += (double)run[ci][j];
                     }
                 }
             } else {
 #pragma unroll
             for (int ci = 0; ci < NC; ++ci) {
                 const int c = grp + 2 * ci;
-                float (&v)[32] = reinterpret_cast<float (&)[32]>(run[ci]);
+                float (&v)[32] = run[ci];
                 {
                     const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c * 32);
 #pragma unroll

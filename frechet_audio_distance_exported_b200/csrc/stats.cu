@@ -273,7 +273,7 @@ static int stats_accumulate_t(fadb_handle* h, const TIn* emb, int64_t n, int d, 
         stats_colsum_kernel<TIn><<<grid, 256, 0, st>>>(emb, n, d, ld, shift, acc, rows_per);
         h->launches++;
     }
-    if (std::is_same<TIn, float>::value && h->tc_syrk && d >= 512 && d % 128 == 0 && n >= 1024) {
+    if (std::is_same<TIn, float>::value && h->tc_syrk && d >= 512 && d % 128 == 0 && n >= 8192) {
         // second moments on the tensor cores (the packed linear-layer path needs d % 128 == 0)
         FADB_CHECK(stats_syrk_tensor(h, reinterpret_cast<const float*>(emb), n, d, ld, shift, acc + 1 + d, st));
     } else {
