@@ -94,7 +94,11 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kMaxStages = 8;
-    static constexpr int kTmemCols = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
+    // accumulators in tensor memory: 2 for BN = 256, 4 for BN <= 128.  With one accumulation segment per <= 64 MMAs the
+    // MMA warp may run up to kAcc - 1 segments ahead of the epilogue's TMEM reads (measured on the statistics GEMM, 16-MMA
+    // segments: the commit -> read -> hand-back round trip is ~4000 cycles, four times the MMAs of such a segment)
+    static constexpr int kAcc = BN == 256 ? 2 : 4;
+    static constexpr int kTmemCols = kAcc * BN;   // 256 / 512 / 512: powers of two >= 32
     static constexpr int kExtraBytes = 512 /*barriers*/ + 1024 /*alignment slack*/;
     static constexpr int kMaxSmemBytes = 232448;                      // 227 KB: the per-CTA opt-in maximum
     static int stages_for(int budget_bytes) {
@@ -134,12 +138,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + res_bytes + kStages * stage_pitch + bring_bytes);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages]
-    const uint32_t bar_tfull = bar_empty + 8 * kStages;              // [2]
-    const uint32_t bar_tempty = bar_tfull + 16;                      // [2]
-    const uint32_t bar_bres = bar_tempty + 16;                       // [1]
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;              // [4]
+    const uint32_t bar_tempty = bar_tfull + 32;                      // [4]
+    const uint32_t bar_bres = bar_tempty + 32;                       // [1]
     const uint32_t bar_bfull = bar_bres + 8;                         // [8]  halo mode B ring
     const uint32_t bar_bempty = bar_bfull + 64;                      // [8]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5 + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 9 + 16);
     // the layer's whole bias vector lives in shared memory (bars + 512 B): the epilogue reads it with broadcast
     // LDS instead of exposing a global-load round trip per 32-column chunk (ncu: 16 % of all stall samples sat on
     // the first FADD after the bias __ldg in the short-K layers)
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster);  // multicast mode: both CTAs' MMA warps release a stage
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
             mbar_init(bar_tempty + 8 * s, PAIR ? 16 : 8);        // one arrive per epilogue warp (of both CTAs in pair mode)
         }
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         // ======================= MMA issuer, halo mode =======================
         constexpr uint32_t idesc = (1u << 4) | kFmtBits | (uint32_t(BN >> 3) << 17) |
                                    (uint32_t((PAIR ? 2 * kTileM : kTileM) >> 4) << 24);
-        int stage = 0, bs = 0, gs = 0;                          // gs = running segment count: accumulator gs & 1
+        int stage = 0, bs = 0, gs = 0;                          // gs = running segment count: accumulator gs % kAcc
         uint32_t phase = 0, bphase = 0;
         const bool issuer = !PAIR || crank == 0;                // pair mode: the leader issues for both CTAs
         if (issuer && p.resb && unit0 < p.num_units) {
@@ -377,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             // in a rolled loop: ~500 cycles of issue overhead per tap, 4x the MMA time at N = 64.)
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
                 if (seg_left == 0) {                                        // open the next accumulation segment
-                    as = gs & 1;
-                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs >> 1) & 1u) ^ 1u, p.err_flag);
+                    as = gs % Cfg::kAcc;
+                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);
                     tc_fence_after();
                     tmem_d = tmem_base + as * BN;
                     seg_left = p.seg_len;
@@ -447,9 +451,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
                 if (skip_unit(unit)) continue;
                 for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
-                    const int as = gs & 1;
+                    const int as = gs % Cfg::kAcc;
                     const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
-                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs >> 1) & 1u) ^ 1u, p.err_flag);   // both CTAs' epilogues drained it
+                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);   // both CTAs' epilogues drained it
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
                     for (int kb = k0; kb < k1; ++kb) {
@@ -483,9 +487,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
                 if (skip_unit(unit)) continue;
                 for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
-                    const int as = gs & 1;
+                    const int as = gs % Cfg::kAcc;
                     const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
-                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs >> 1) & 1u) ^ 1u, p.err_flag);   // epilogue drained this accumulator
+                    mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
                     for (int kb = k0; kb < k1; ++kb) {
@@ -562,8 +566,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 for (int j = 0; j < 32; ++j) run[ci][j] = 0;
 #pragma unroll 1
             for (int seg = 0; seg < p.nseg; ++seg, ++gs) {
-                const int as = gs & 1;
-                mbar_wait(bar_tfull + 8 * as, ((uint32_t)gs >> 1) & 1u, p.err_flag);
+                const int as = gs % Cfg::kAcc;
+                mbar_wait(bar_tfull + 8 * as, ((uint32_t)gs / Cfg::kAcc) & 1u, p.err_flag);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN + grp * 32;
 #pragma unroll

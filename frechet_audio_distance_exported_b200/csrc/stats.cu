@@ -131,22 +131,26 @@ __global__ void __launch_bounds__(256, 1) stats_syrk_kernel(const TIn* __restric
 // 1e6 x 2048 (BASELINE configs[4]); the fp64 kernel above stays for d < 512 and as the checker.
 constexpr int kSyrkChunkRows = 65536;
 
-// x [rows][ld] -> hi / lo [d][stride] fp16 (kpad <= stride columns written) of y = x - K', K' = the chunk's own column mean (csum[1 + c] / rows, fp64), zero
-// beyond the chunk's rows.  Centring on the chunk mean keeps the products free of the mean^2 term (the fp32 chains
-// inside the MMA truncate: a bias relative to the SECOND MOMENT, which the subtraction of mu mu^T would amplify).
-// 64 features x 64 samples per CTA through shared memory; every thread writes 16 consecutive samples of one feature
-// (two 16-byte stores per plane), a warp covers 8 complete 128-byte rows.
+// x [rows][ld] -> hi / lo [d][stride] fp16 (kpad <= stride columns written) of y = x - K', zero beyond the chunk's rows,
+// and ysum[c] += sum of y over the chunk (fp64).  K' = the column mean of the chunk's FIRST rows0 rows (csum0[1 + c] /
+// rows0): any centre near the mean keeps the products free of the mean^2 term (the fp32 chains inside the MMA truncate: a
+// bias relative to the SECOND MOMENT, which the later subtraction of mu mu^T would amplify), and a provisional one lets
+// the chunk be read once.  64 features x 64 samples per CTA through shared memory; every thread writes 16 consecutive
+// samples of one feature (two 16-byte stores per plane), a warp covers 8 complete 128-byte rows.
 template <typename TIn>
 __global__ void __launch_bounds__(256) syrk_split_transpose_kernel(const TIn* __restrict__ x, long long rows, int d,
-                                                                   long long ld, const double* __restrict__ csum,
-                                                                   int stride, int kpad, __half* __restrict__ hi,
-                                                                   __half* __restrict__ lo) {
+                                                                   long long ld, const double* __restrict__ csum0,
+                                                                   long long rows0, int stride, int kpad,
+                                                                   __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                   double* __restrict__ ysum) {
     __shared__ float tile[64][65];                          // [sample][feature]
+    __shared__ double part[4][64];
     const int c0 = blockIdx.x * 64;
     const long long r0 = (long long)blockIdx.y * 64;
     {
         const int f = threadIdx.x & 63, c = c0 + f;
-        const double kp = (c < d) ? csum[1 + c] / (double)rows : 0.0;
+        const double kp = (c < d) ? csum0[1 + c] / (double)rows0 : 0.0;
+        double acc = 0.0;
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {
             const int sl = (threadIdx.x >> 6) + 4 * i;
@@ -154,40 +158,45 @@ __global__ void __launch_bounds__(256) syrk_split_transpose_kernel(const TIn* __
             float v = 0.f;
             if (r < rows && c < d) v = (float)((double)__ldg(x + r * ld + c) - kp);
             tile[sl][f] = v;
+            acc += (double)v;
         }
+        part[threadIdx.x >> 6][f] = acc;
     }
     __syncthreads();
-    const int f = threadIdx.x >> 2, part = threadIdx.x & 3, c = c0 + f;
-    if (c < d && r0 + 16 * part < kpad) {
+    if (threadIdx.x < 64 && c0 + threadIdx.x < d)
+        atomicAdd(ysum + c0 + threadIdx.x, (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]));
+    const int f = threadIdx.x >> 2, pt = threadIdx.x & 3, c = c0 + f;
+    if (c < d && r0 + 16 * pt < kpad) {
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float v0 = fminf(fmaxf(tile[16 * part + 2 * k][f], -65504.f), 65504.f);
-            const float v1 = fminf(fmaxf(tile[16 * part + 2 * k + 1][f], -65504.f), 65504.f);
+            const float v0 = fminf(fmaxf(tile[16 * pt + 2 * k][f], -65504.f), 65504.f);
+            const float v1 = fminf(fmaxf(tile[16 * pt + 2 * k + 1][f], -65504.f), 65504.f);
             const __half2 h = __floats2half2_rn(v0, v1);
             const __half2 l = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
             ph[k] = *reinterpret_cast<const uint32_t*>(&h);
             pl[k] = *reinterpret_cast<const uint32_t*>(&l);
         }
-        uint4* dh = reinterpret_cast<uint4*>(hi + (size_t)c * stride + r0 + 16 * part);
-        uint4* dl = reinterpret_cast<uint4*>(lo + (size_t)c * stride + r0 + 16 * part);
+        uint4* dh = reinterpret_cast<uint4*>(hi + (size_t)c * stride + r0 + 16 * pt);
+        uint4* dl = reinterpret_cast<uint4*>(lo + (size_t)c * stride + r0 + 16 * pt);
         dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
         dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
     }
 }
 
-// S (fp64, upper 128 x 128 tiles) += rows * delta delta^T, delta = K' - K (chunk mean minus the caller's common shift):
-// sum (x-K)(x-K)^T = sum y y^T + rows delta delta^T because sum y = 0 for y = x - K'.  (sum y y^T is added by the GEMM's
-// own epilogue.)
-__global__ void syrk_rank1_kernel(int d, const double* __restrict__ csum, long long rows,
-                                  const double* __restrict__ shift, double* __restrict__ S) {
+// S (fp64, upper 128 x 128 tiles) += s delta^T + delta s^T + rows delta delta^T with s = sum y (ysum), delta = K' - K
+// (provisional chunk centre minus the caller's common shift):
+//   sum (x-K)(x-K)^T = sum (y+delta)(y+delta)^T = sum y y^T + s delta^T + delta s^T + rows delta delta^T,
+// and sum y y^T is added by the GEMM's own epilogue.
+__global__ void syrk_rank2_kernel(int d, const double* __restrict__ csum0, long long rows0, const double* __restrict__ ysum,
+                                  long long rows, const double* __restrict__ shift, double* __restrict__ S) {
     const size_t total = (size_t)d * d;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / d), j = (int)(e % d);
         if (i / TS <= j / TS) {
-            const double di = csum[1 + i] / (double)rows - (shift ? shift[i] : 0.0);
-            const double dj = csum[1 + j] / (double)rows - (shift ? shift[j] : 0.0);
-            S[e] += (double)rows * di * dj;
+            const double di = csum0[1 + i] / (double)rows0 - (shift ? shift[i] : 0.0);
+            const double dj = csum0[1 + j] / (double)rows0 - (shift ? shift[j] : 0.0);
+            S[e] += ysum[i] * dj + di * ysum[j] + (double)rows * di * dj;
         }
     }
 }
@@ -203,23 +212,26 @@ static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d,
     if (n < chunk) chunk = ((n + 63) / 64) * 64;
     const int64_t stride = chunk + 64;
     const size_t plane = (size_t)d * stride;                                  // fp16 elements per plane
-    const size_t csum_bytes = ((size_t)(1 + d) * sizeof(double) + 255) / 256 * 256;
-    FADB_CHECK(h->ws_syrk.reserve(2 * plane * sizeof(__half) + csum_bytes + 256));
-    double* csum = h->ws_syrk.as<double>();
-    __half* hi = reinterpret_cast<__half*>(h->ws_syrk.as<char>() + csum_bytes);
+    const size_t vec_bytes = ((size_t)(2 + 2 * d) * sizeof(double) + 255) / 256 * 256;    // csum0 [1 + d] | ysum [d]
+    FADB_CHECK(h->ws_syrk.reserve(2 * plane * sizeof(__half) + vec_bytes + 256));
+    double* csum0 = h->ws_syrk.as<double>();
+    double* ysum = csum0 + 1 + d;
+    __half* hi = reinterpret_cast<__half*>(h->ws_syrk.as<char>() + vec_bytes);
     __half* lo = hi + plane;
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
+        const int64_t rows0 = rows < 512 ? rows : 512;
         const int kpad = (int)(((rows + 63) / 64) * 64);
-        // chunk column sums (fp64) -> the chunk's own centre K'
-        FADB_CUDA_CHECK(cudaMemsetAsync(csum, 0, (size_t)(1 + d) * sizeof(double), st));
+        // provisional centre: column sums (fp64) of the chunk's first rows
+        FADB_CUDA_CHECK(cudaMemsetAsync(csum0, 0, (size_t)(2 + 2 * d) * sizeof(double), st));
         {
-            const int rows_per = 256;
-            dim3 g((d + 255) / 256, (unsigned)((rows + rows_per - 1) / rows_per));
-            stats_colsum_kernel<float><<<g, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, nullptr, csum, rows_per);
+            const int rows_per = 32;
+            dim3 g((d + 255) / 256, (unsigned)((rows0 + rows_per - 1) / rows_per));
+            stats_colsum_kernel<float><<<g, 256, 0, st>>>(emb + r0 * ld, rows0, d, ld, nullptr, csum0, rows_per);
         }
         dim3 grid((d + 63) / 64, (unsigned)(kpad / 64));
-        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, csum, (int)stride, kpad, hi, lo);
+        syrk_split_transpose_kernel<float><<<grid, 256, 0, st>>>(emb + r0 * ld, rows, d, ld, csum0, rows0, (int)stride, kpad,
+                                                                 hi, lo, ysum);
         PackedLayer L;
         L.N = d; L.K = kpad; L.Cin = kpad; L.taps = 1; L.f16 = 1;
         L.w_hi = reinterpret_cast<__nv_bfloat16*>(hi);
@@ -232,11 +244,11 @@ static int stats_syrk_tensor(fadb_handle* h, const float* emb, int64_t n, int d,
         io.out_f64 = S;
         io.row_stride = stride;
         io.syrk = 1;
-        io.seg_blocks = 4;              // 16-MMA chains: truncation bias ~3e-7 of the centred second moment
+        io.seg_blocks = 4;              // 16-MMA chains: truncation bias ~1e-6 of the centred second moment
         FADB_CHECK(launch_gemm_layer(h, L, io, st));
         int g = (int)(((size_t)d * d + 255) / 256);
         if (g > 148 * 16) g = 148 * 16;
-        syrk_rank1_kernel<<<g, 256, 0, st>>>(d, csum, rows, shift, S);
+        syrk_rank2_kernel<<<g, 256, 0, st>>>(d, csum0, rows0, ysum, rows, shift, S);
         h->launches += 3;
     }
     FADB_CUDA_CHECK(cudaGetLastError());
