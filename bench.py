@@ -292,7 +292,17 @@ def stats_frechet_microbench(eng, cpu: bool):
         frechet[key] = {"gpu_ms": ms_fr, "n_per_set": n, "fad": float(fr[0])}
         if n != 1000:
             stats[key] = {"gpu_ms_both_sets": ms_stats, "n_per_set": n, "read_gbs": 2 * n * d * 4 / ms_stats / 1e6,
-                          "flops_per_s_T": 2 * n * d * (d + 1) / ms_stats / 1e9}
+                          "flops_per_s_T": 2 * n * d * (d + 1) / ms_stats / 1e9, "kernel": "fp64 DFMA syrk (default)"}
+            if d >= 512:
+                # opt-in tensor-core syrk (split-fp16 tcgen05 GEMM, fadb_set_tensor_syrk): speed and what it costs in accuracy
+                eng.set_tensor_syrk(True)
+                ms_tc, ((_, t1), (_, t2)) = _gpu_ms(stats_both)
+                eng.set_tensor_syrk(False)
+                frt = eng.frechet(mu1, t1, mu2, t2)
+                stats[key]["tensor_core"] = {
+                    "gpu_ms_both_sets": ms_tc, "flops_per_s_T": 2 * n * d * (d + 1) / ms_tc / 1e9,
+                    "sigma_rel_err_vs_fp64_kernel": float((t1 - s1).abs().max() / s1.abs().max()),
+                    "fad_rel_err_vs_fp64_kernel": abs(float(frt[0]) - float(fr[0])) / abs(float(fr[0]))}
         if cpu:
             h1, h2 = x1[:20000].cpu().numpy(), x2[:20000].cpu().numpy()       # bounded CPU sample
             t0 = time.perf_counter()

@@ -516,6 +516,12 @@ int fadb_set_precision(fadb_handle* h, int prec) {
     return FADB_OK;
 }
 
+int fadb_set_tensor_syrk(fadb_handle* h, int on) {
+    if (!h) { set_error("fadb_set_tensor_syrk: NULL handle"); return FADB_E_INVALID; }
+    h->tc_syrk = on ? 1 : 0;
+    return FADB_OK;
+}
+
 int fadb_set_max_batch(fadb_handle* h, int max_items) {
     if (!h || max_items < 1 || max_items > 65535) { set_error("max_batch must be in [1, 65535]"); return FADB_E_INVALID; }
     h->max_batch = max_items;

@@ -69,6 +69,11 @@ class Engine:
         if self.weights_loaded and (self._packed[0] != fmt or (lo and not self._packed[1])):
             self.load_state_dict(self._sd)
 
+    def set_tensor_syrk(self, on: bool) -> None:
+        """Second moments of large sets (>= 8192 rows, d >= 512) on the tensor cores: ~8x faster, covariance to ~1e-6
+        instead of fp64-exact.  Off by default (include/fadb.h: fadb_set_tensor_syrk)."""
+        check(self.lib.fadb_set_tensor_syrk(self.h, int(bool(on))))
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """Hand the reference modules' state_dict (VGGishCore / PANNCore key names) to the packer."""
         check(self.lib.fadb_weights_begin(self.h, self.model_id))

@@ -67,6 +67,12 @@ void fadb_destroy(fadb_handle* h);
 /* Packed weights are stored in the 16-bit format of the precision that was current at fadb_weights_commit (bf16 or
  * fp16): after switching between the two families the weights must be committed again (FADB_E_STATE otherwise). */
 int fadb_set_precision(fadb_handle* h, int prec);
+/* Statistics of large embedding sets (>= 8192 rows per call, d >= 512 and a multiple of 128) on the tensor cores:
+ * sum (x-K)(x-K)^T as a split-fp16 tcgen05 GEMM (3 MMAs per product) instead of the fp64 DFMA kernel.  About 8x
+ * faster at d = 2048; the covariance is then accurate to ~1e-6 (truncation inside the MMA's fp32 accumulation)
+ * instead of ~1e-14.  Off by default: the reference computes np.cov in fp64 (fad.py:495), and the Frechet distance
+ * of two SIMILAR sets amplifies a covariance error by tr(S) / FAD. */
+int fadb_set_tensor_syrk(fadb_handle* h, int on);
 /* max patches (VGGish) / clips (CNN14) per internal batch; sizes the activation workspace */
 int fadb_set_max_batch(fadb_handle* h, int max_items);
 

@@ -619,17 +619,17 @@ def test_two_handles_on_one_device_are_independent(vgg_sd):
 
 
 @pytest.mark.parametrize("n,d", [(9000, 512), (20000, 2048), (70000, 640)])
-def test_tensor_core_syrk_matches_fp64_kernel(monkeypatch, n, d):
+def test_tensor_core_syrk_matches_fp64_kernel(n, d):
     """Second moments of >= 8192 rows at d >= 512 run as a split-fp16 tcgen05 GEMM (stats.cu: rows centred on the chunk
     mean, 3 MMAs per product, 16-MMA accumulation chains, tiles below the diagonal skipped, finished tiles added to the
-    fp64 statistic); the fp64 DFMA kernel (FADB_TC_SYRK=0) is the checker.  What is left is the truncation inside
+    fp64 statistic) when Engine.set_tensor_syrk(True) asks for it; the default fp64 DFMA kernel is the checker.  What is left is the truncation inside
     tcgen05.mma's fp32 accumulation: measured 1.0e-6 of the covariance (norm-wise), 2e-6 (d = 2048) .. 2e-5 (d = 512) of
     the Frechet distance, against the north-star's 1e-4.  Several row chunks incl. a ragged one; d = 640 = an odd number
     of M tiles for the CTA pairs."""
     from frechet_audio_distance_exported_b200 import Engine
     tc = Engine("vggish")
-    monkeypatch.setenv("FADB_TC_SYRK", "0")
-    ref = Engine("vggish")
+    tc.set_tensor_syrk(True)
+    ref = Engine("vggish")                                   # default: the fp64 kernel
     out = {}
     for name, eng in (("tc", tc), ("fp64", ref)):
         res = []
@@ -642,4 +642,6 @@ def test_tensor_core_syrk_matches_fp64_kernel(monkeypatch, n, d):
     for s_ in (0, 1):
         assert relerr(out["tc"][0][s_][1].cpu().numpy(), out["fp64"][0][s_][1].cpu().numpy()) < 3e-6
         assert relerr(out["tc"][0][s_][0].cpu().numpy(), out["fp64"][0][s_][0].cpu().numpy()) < 1e-12
-    assert abs(out["tc"][1] - out["fp64"][1]) / abs(out["fp64"][1]) < 5e-5
+    # FAD = tr S1 + tr S2 - 2 tr sqrt(S1 S2) + |dmu|^2 cancels: its absolute error scales with the traces
+    tr = float(out["fp64"][0][0][1].diagonal().sum() + out["fp64"][0][1][1].diagonal().sum())
+    assert abs(out["tc"][1] - out["fp64"][1]) < 5e-6 * tr

@@ -12,9 +12,8 @@ from oracle import networks, stats
 
 cpu = "--no-cpu" not in sys.argv
 eng = Engine("vggish")
-os.environ["FADB_TC_SYRK"] = "0"
-eng64 = Engine("vggish")                                 # the fp64 DFMA syrk as the checker of the tensor-core path
-os.environ.pop("FADB_TC_SYRK")
+eng.set_tensor_syrk(True)                                # the opt-in tensor-core syrk (d >= 512, >= 8192 rows)
+eng64 = Engine("vggish")                                 # the default fp64 DFMA syrk: the checker of the tensor-core path
 dev = eng.device
 
 

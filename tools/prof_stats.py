@@ -9,6 +9,7 @@ from frechet_audio_distance_exported_b200.engine import Engine
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 eng = Engine("vggish")
+eng.set_tensor_syrk(True)
 x = torch.randn(n, d, device="cuda") + 0.5
 for _ in range(2):
     acc = eng.new_acc(d)
