@@ -43,7 +43,7 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
 // x [B, Ht, Wf, C] bf16 (hi + optional lo) -> mean over Wf, then max over Ht + mean over Ht  (pann.py:263-268)
 __global__ void cnn14_global_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                          int Ht, int Wf, int C, __nv_bfloat16* __restrict__ ohi,
-                                         __nv_bfloat16* __restrict__ olo, int f16) {
+                                         __nv_bfloat16* __restrict__ olo, int f16, uint8_t* __restrict__ o8) {
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -64,6 +64,11 @@ __global__ void cnn14_global_pool_kernel(const __nv_bfloat16* __restrict__ hi, c
     const float r = mx + sum / (float)Ht;
     if (f16) {
         reinterpret_cast<__half*>(ohi)[(size_t)b * C + c] = __float2half_rn(fminf(r, 65504.f));
+        if (o8) {
+            uint16_t q;
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(q) : "f"(0.f), "f"(r));
+            o8[(size_t)b * C + c] = (uint8_t)(q & 0xffu);
+        }
         return;
     }
     const __nv_bfloat16 h = __float2bfloat16_rn(r);
@@ -90,11 +95,12 @@ __global__ void l2_normalize_kernel(float* __restrict__ x, int d) {   // F.norma
 }
 
 int launch_cnn14_global_pool(fadb_handle* h, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t B, int Ht,
-                             int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+                             int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, uint8_t* out8, cudaStream_t st) {
     dim3 grid((C + 255) / 256, (unsigned)B);
     const bool x3 = h->precision == FADB_PREC_BF16X3;
     cnn14_global_pool_kernel<<<grid, 256, 0, st>>>(x_hi, x3 ? x_lo : nullptr, Ht, Wf, C, out_hi, x3 ? out_lo : nullptr,
-                                                   (int)prec_is_f16(h->precision));
+                                                   (int)prec_is_f16(h->precision),
+                                                   (h->precision == FADB_PREC_FP16X2 && h->lo_fp8) ? out8 : nullptr);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
@@ -113,6 +119,7 @@ static void free_layers(fadb_handle* h) {
     for (auto& L : h->layers) {
         if (L.w_hi) cudaFree(L.w_hi);
         if (L.w_lo) cudaFree(L.w_lo);
+        if (L.w8) cudaFree(L.w8);
         if (L.bias) cudaFree(L.bias);
     }
     h->layers.clear();
@@ -166,6 +173,10 @@ static int add_layer(fadb_handle* h, const float* w, int Cout, int Cin, int ksiz
     if (want_lo) FADB_CUDA_CHECK(cudaMalloc(&L.w_lo, n * sizeof(__nv_bfloat16)));
     FADB_CUDA_CHECK(cudaMalloc(&L.bias, (size_t)Cout * sizeof(float)));
     FADB_CHECK(pack_conv_weight(h, w, Cout, Cin, ksize, scale, L.w_hi, L.w_lo, L.f16 != 0, st));
+    if (h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && Cin % 128 == 0) {      // e4m3 low-order plane (gemm_tc.cu lo8)
+        FADB_CUDA_CHECK(cudaMalloc(&L.w8, n));
+        FADB_CHECK(pack_conv_weight_lo8(h, w, Cout, Cin, ksize, scale, L.w8, &L.lo_scale, st));
+    }
     if (bias_or_shift)
         FADB_CUDA_CHECK(cudaMemcpyAsync(L.bias, bias_or_shift, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
     else
@@ -288,6 +299,13 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
     FADB_CHECK(h->ws_act[1].reserve(plane * nplanes * sizeof(__nv_bfloat16)));
     __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
     __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
+    uint8_t* a8[2] = {nullptr, nullptr};                                    // e4m3 copies (fp16x2 with the e4m3 lo pass)
+    if (h->precision == FADB_PREC_FP16X2 && h->lo_fp8) {
+        FADB_CHECK(h->ws_act8[0].reserve(plane));
+        FADB_CHECK(h->ws_act8[1].reserve(plane));
+        a8[0] = h->ws_act8[0].as<uint8_t>(); a8[1] = h->ws_act8[1].as<uint8_t>();
+    }
+    const uint8_t* in8 = nullptr;                                           // conv1's 64-channel output has no e4m3 copy
     const int B = (int)P;
     struct Step { int H, W, Cin, pool; };
     static const Step steps[5] = {{48, 32, 64, 1}, {24, 16, 128, 0}, {24, 16, 256, 1}, {12, 8, 256, 0}, {12, 8, 512, 1}};
@@ -300,9 +318,10 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
         io.B = B; io.H = steps[i].H; io.W = steps[i].W; io.Cin = steps[i].Cin;
         io.taps = 9; io.relu = 1; io.pool = steps[i].pool;
         io.out_hi = a[cur]; io.out_lo = l[cur];
+        io.in8 = in8; io.out8 = a8[cur];
         io.use_lo_weights = (h->x2_mask >> i) & 1u;
         FADB_CHECK(launch_gemm_layer(h, h->layers[i], io, st));
-        in_hi = a[cur]; in_lo = l[cur];
+        in_hi = a[cur]; in_lo = l[cur]; in8 = a8[cur];
         cur ^= 1;
     }
     // NHWC flatten (vggish.py:91-94) is the memory order already: [P, 6*4*512]
@@ -314,9 +333,10 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
         io.taps = 1; io.relu = (i < 2); io.pool = 0;
         if (i < 2) { io.out_hi = a[cur]; io.out_lo = l[cur]; }
         else io.out_f32 = emb;                                                          // no final ReLU, vggish.py:76-77
+        io.in8 = in8; io.out8 = a8[cur];
         io.use_lo_weights = (h->x2_mask >> (5 + i)) & 1u;
         FADB_CHECK(launch_gemm_layer(h, h->layers[5 + i], io, st));
-        in_hi = a[cur]; in_lo = l[cur];
+        in_hi = a[cur]; in_lo = l[cur]; in8 = a8[cur];
         cur ^= 1;
     }
     return FADB_OK;
@@ -374,6 +394,14 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
     FADB_CHECK(h->ws_act[1].reserve(plane * nplanes * sizeof(__nv_bfloat16)));
     __nv_bfloat16* a[2] = {h->ws_act[0].as<__nv_bfloat16>(), h->ws_act[1].as<__nv_bfloat16>()};
     __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
+    uint8_t* a8[2] = {nullptr, nullptr};                                    // e4m3 copies (fp16x2 with the e4m3 lo pass)
+    if (h->precision == FADB_PREC_FP16X2 && h->lo_fp8) {
+        // the 64-channel maps of block 1 need none: the largest map with a copy is block 2's [B, T/2, 32, 128]
+        FADB_CHECK(h->ws_act8[0].reserve(plane / 2));
+        FADB_CHECK(h->ws_act8[1].reserve(plane / 2));
+        a8[0] = h->ws_act8[0].as<uint8_t>(); a8[1] = h->ws_act8[1].as<uint8_t>();
+    }
+    bool have8 = false;                                                     // does a8[cur] hold the current activations?
     FADB_CHECK(launch_conv1_cnn14(h, feats, B, T, a[0], l[0], st));                     // [B,T,64,64]
     int cur = 0, H = T, W = 64, C = 64, li = 0;
     for (int blk = 1; blk <= 6; ++blk) {
@@ -385,8 +413,11 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
             io.taps = 9; io.relu = 1;
             io.pool = (cv == 2 && blk < 6) ? 2 : 0;                                     // avg_pool2d, pann.py:192,255-260
             io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+            io.in8 = have8 ? a8[cur] : nullptr;
+            io.out8 = (h->layers[li].N % 128 == 0) ? a8[cur ^ 1] : nullptr;
             io.use_lo_weights = (h->x2_mask >> li) & 1u;
             FADB_CHECK(launch_gemm_layer(h, h->layers[li], io, st));
+            have8 = io.out8 != nullptr;
             C = h->layers[li].N;
             ++li;
             cur ^= 1;
@@ -394,13 +425,14 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
         }
     }
     // global pooling -> [B, 2048]
-    FADB_CHECK(launch_cnn14_global_pool(h, a[cur], l[cur], B, H, W, C, a[cur ^ 1], l[cur ^ 1], st));
+    FADB_CHECK(launch_cnn14_global_pool(h, a[cur], l[cur], B, H, W, C, a[cur ^ 1], l[cur ^ 1], a8[cur ^ 1], st));
     cur ^= 1;
     const bool clap = (h->model == FADB_MODEL_CLAP);
     {
         LayerIO io;
         io.in_hi = a[cur]; io.in_lo = l[cur];
         io.B = 1; io.H = 1; io.W = B; io.Cin = 2048; io.taps = 1; io.relu = 1; io.pool = 0;     // pann.py:271
+        io.in8 = a8[cur]; io.out8 = a8[cur ^ 1];
         if (clap) { io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1]; }
         else io.out_f32 = emb;
         FADB_CHECK(launch_gemm_layer(h, h->layers[li++], io, st));
@@ -411,11 +443,13 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
         io.in_hi = a[cur]; io.in_lo = l[cur];
         io.B = 1; io.H = 1; io.W = B; io.Cin = 2048; io.taps = 1; io.relu = 1; io.pool = 0;
         io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
+        io.in8 = a8[cur]; io.out8 = a8[cur ^ 1];
         FADB_CHECK(launch_gemm_layer(h, h->layers[li++], io, st));
         cur ^= 1;
         LayerIO io2;
         io2.in_hi = a[cur]; io2.in_lo = l[cur];
         io2.B = 1; io2.H = 1; io2.W = B; io2.Cin = 512; io2.taps = 1; io2.relu = 0; io2.pool = 0;
+        io2.in8 = a8[cur];
         io2.out_f32 = emb;
         FADB_CHECK(launch_gemm_layer(h, h->layers[li++], io2, st));
         FADB_CHECK(launch_l2_normalize(h, emb, B, 512, st));
@@ -480,6 +514,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_FUSED_FRONT")) h->fused_front = atoi(e);
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
     if (const char* e = getenv("FADB_TC_SYRK")) h->tc_syrk = atoi(e);
+    if (const char* e = getenv("FADB_LO_FP8")) h->lo_fp8 = atoi(e);
     if (const char* e = getenv("FADB_X2_MASK")) h->x2_mask = (unsigned)strtoul(e, nullptr, 0);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
@@ -497,6 +532,7 @@ void fadb_destroy(fadb_handle* h) {
     frontend_release(h);
     h->weight_pool.release();
     h->ws_feats.release(); h->ws_act[0].release(); h->ws_act[1].release(); h->ws_misc.release();
+    h->ws_act8[0].release(); h->ws_act8[1].release();
     h->ws_syrk.release();
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -825,11 +861,18 @@ int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, i
     }
     L.f16 = f16 ? 1 : 0;
     if (rc == FADB_OK) rc = pack_conv_weight(h, w_dev, Cout, Cin, ksize, nullptr, L.w_hi, L.w_lo, f16, st);
+    uint8_t* x8 = nullptr;
+    if (rc == FADB_OK && h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && Cin % 128 == 0) {
+        if (cudaMalloc(&x8, n_in) != cudaSuccess || cudaMalloc(&L.w8, nw) != cudaSuccess) { set_error("cudaMalloc failed"); rc = FADB_E_NOMEM; }
+        if (rc == FADB_OK) rc = quantize_e4m3(h, x, (int64_t)n_in, x8, st);
+        if (rc == FADB_OK) rc = pack_conv_weight_lo8(h, w_dev, Cout, Cin, ksize, nullptr, L.w8, &L.lo_scale, st);
+    }
     L.bias = const_cast<float*>(bias_dev);
     if (rc == FADB_OK) {
         LayerIO io;
         io.in_hi = xh; io.in_lo = xl; io.B = B; io.H = H; io.W = W; io.Cin = Cin;
         io.taps = L.taps; io.relu = relu; io.pool = pool; io.out_f32 = out;
+        io.in8 = x8;
         rc = launch_gemm_layer(h, L, io, st);
     }
     cudaError_t e = cudaStreamSynchronize(st);
@@ -837,6 +880,8 @@ int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, i
     if (xl) cudaFree(xl);
     if (L.w_hi) cudaFree(L.w_hi);
     if (L.w_lo) cudaFree(L.w_lo);
+    if (L.w8) cudaFree(L.w8);
+    if (x8) cudaFree(x8);
     if (rc != FADB_OK) return rc;
     if (e != cudaSuccess) { set_error("debug conv layer failed: %s", cudaGetErrorString(e)); return FADB_E_CUDA; }
     return check_device_flag(h);

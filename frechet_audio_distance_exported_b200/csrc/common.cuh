@@ -80,6 +80,8 @@ struct PackedLayer {
     int f16 = 0;           // planes hold IEEE fp16 instead of bf16
     __nv_bfloat16* w_hi = nullptr;
     __nv_bfloat16* w_lo = nullptr;
+    uint8_t* w8 = nullptr;   // fp16x2: e4m3((w - fp16(w)) / lo_scale), [N][K] K-major, when Cin % 128 == 0 (else nullptr)
+    float lo_scale = 1.f;    // power of two; the e4m3 pass's sums are multiplied by it
     float* bias = nullptr;   // [N] (folded BN shift or conv/linear bias)
 };
 
@@ -119,6 +121,8 @@ struct fadb_handle {
     int gemm_cluster_size = 2;      // CTAs per cluster: 2 or 4
     int gemm_pair_halo = 1;         // CTA pairs for the halo-mode layers too (CNN14 blocks 1-4: +10 %)
     int gemm_twocta = 1;            // clusters of 2: 1 = cta_group::2 MMAs (M = 256 across the pair) instead of weight multicast
+    int lo_fp8 = 1;                 // fp16x2: the low-order weight pass runs in e4m3 at twice the fp16 rate where Cin % 128 == 0
+                                    // (FADB_LO_FP8=0: every lo pass in fp16)
     unsigned x2_mask = 0xffffffffu; // fp16x2: bit i = tensor-core layer i multiplies the lo weight plane too (FADB_X2_MASK)
     int model = -1;                 // model whose weights are committed
     bool weights_ready = false;
@@ -142,6 +146,7 @@ struct fadb_handle {
     fadb::DevBuf ws_a1[1];      // conv1 output (input of the first tensor-core layer)
     fadb::DevBuf ws_feats;      // fp32 features of one batch
     fadb::DevBuf ws_act[2];     // ping-pong bf16 activations (hi plane followed by lo plane)
+    fadb::DevBuf ws_act8[2];    // fp16x2: e4m3 copies of the same activations
     fadb::DevBuf ws_misc;       // pooled vectors etc.
     fadb::DevBuf ws_frechet;    // fp64 workspace of fadb_frechet
     fadb::DevBuf ws_stats;      // fp64 workspace of fadb_fad_from_pcm_host
@@ -197,6 +202,8 @@ int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int 
 struct LayerIO {
     const __nv_bfloat16* in_hi = nullptr;
     const __nv_bfloat16* in_lo = nullptr;     // may be null (bf16 mode)
+    const uint8_t* in8 = nullptr;              // fp16x2: e4m3 copy of the input (for the e4m3 low-order weight pass)
+    uint8_t* out8 = nullptr;                   // fp16x2: where to write the e4m3 copy of the output (Cout % 128 == 0)
     int B = 0, H = 0, W = 0, Cin = 0;          // NHWC input; a linear layer is B=1,H=1,W=rows
     int taps = 9;                              // 9 = 3x3 pad 1, 1 = pointwise / linear
     int relu = 1;
@@ -221,6 +228,11 @@ int gemm_init(fadb_handle* h);
 // (the planes are 16-bit words: bf16, or IEEE fp16 when f16 is set)
 int pack_conv_weight(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
                      __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, bool f16, cudaStream_t st);
+// fp16x2: w8 = e4m3((w - fp16(w)) / lo_scale) in the packed [Cout][tap][Cin] order; *lo_scale (a power of two) is chosen so
+// that the largest residual lands near the top of the e4m3 range.  Synchronises the stream.
+int pack_conv_weight_lo8(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
+                         uint8_t* w8, float* lo_scale, cudaStream_t st);
+int quantize_e4m3(fadb_handle* h, const float* x, int64_t n, uint8_t* out, cudaStream_t st);
 int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo, bool f16,
                       cudaStream_t st);
 int fold_bn(fadb_handle* h, const float* gamma, const float* beta, const float* mean, const float* var, int C,
@@ -228,7 +240,7 @@ int fold_bn(fadb_handle* h, const float* gamma, const float* beta, const float* 
 
 // cnn14 tail (global pooling)  — cnn14.cu
 int launch_cnn14_global_pool(fadb_handle* h, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int64_t B, int Ht,
-                             int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
+                             int Wf, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, uint8_t* out8, cudaStream_t st);
 int launch_l2_normalize(fadb_handle* h, float* x, int64_t rows, int d, cudaStream_t st);
 
 // stats.cu

@@ -41,10 +41,11 @@ namespace fadb {
 // Kernel parameters (tensor maps live in the parameter/constant bank: __grid_constant__)
 // ------------------------------------------------------------------------------------------------
 struct GemmParams {
-    CUtensorMap tmA[2];   // activations hi, lo : dims (C, W, H, B)
-    CUtensorMap tmB[2];   // weights hi, lo     : dims (Ktot, N)
+    CUtensorMap tmA[3];   // activations hi, lo, e4m3 : dims (C, W, H, B)
+    CUtensorMap tmB[3];   // weights hi, lo, e4m3-lo  : dims (Ktot, N)
     CUtensorMap tmH;      // halo mode: activations hi with box (64 ch, 10 px, 18 rows, 1 image)
-    CUtensorMap tmBh[2];  // cluster mode: weights hi, lo with box (64, BN/2): each CTA of a pair loads half (and multicasts it)
+    CUtensorMap tmH8;     // halo mode, e4m3 activations: box (128 ch, 10 px, 18 rows, 1 image)
+    CUtensorMap tmBh[3];  // cluster mode: weights hi, lo, e4m3-lo with box (., BN/2): each CTA of a pair loads half (and multicasts it)
     int W, H, B;
     int BW, BH, BB;       // box; BW*BH*BB == 128
     int tiles_w, tiles_h, tiles_b, tiles_n;
@@ -59,7 +60,16 @@ struct GemmParams {
                           // 3 = A_hi*B_hi, A_lo*B_hi, A_hi*B_lo (bf16x3)
     int N;                // Cout
     int stages;           // smem pipeline depth (runtime: sized from the handle's smem budget)
-    int nkb;              // K blocks (of 64) per tile: npass * taps * cin_blocks
+    int nkb;              // K blocks (128 bytes of K per row) per tile: npass * taps * cin_blocks, or kb0 + taps * cin_blocks1
+    int lo8;              // fp16x2 with the LOW-ORDER weight pass in e4m3: pass 1 multiplies e4m3(activations) by
+                          // e4m3((W - fp16(W)) * 2^s) with kind::f8f6f4 MMAs (twice the fp16 rate) over 128-channel K blocks;
+                          // its segment sums are scaled by lo_scale = 2^-s when the epilogue adds them in
+    int kb0;              // K blocks of pass 0 (taps * cin_blocks)
+    int cin_blocks1;      // channel blocks of pass 1: Cin / 128 when lo8
+    int nseg0;            // accumulation segments of pass 0 (lo8: segments never straddle the pass boundary)
+    int seg_len1;         // segment length of pass 1
+    float lo_scale;
+    uint8_t* out8;        // e4m3 copy of the output (the next layer's pass-1 activations), or nullptr
     int nseg, seg_len;    // accumulation segments per tile and their length (K blocks; halo mode: channel blocks).
                           // Each segment is its own accumulation chain in tensor memory (the two TMEM accumulators
                           // alternate per SEGMENT); the epilogue warps add the segment sums in fp32 registers with
@@ -214,8 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     const int kb_per_pass = p.taps * p.cin_blocks;
     // which activation / weight plane a pass multiplies: npass 1: (0,0); 2: (0,0),(0,1); 3: (0,0),(1,0),(0,1)
-    auto pass_a = [&](int pass) { return (p.npass == 3 && pass == 1) ? 1 : 0; };
-    auto pass_b = [&](int pass) { return (p.npass == 3) ? (pass == 2 ? 1 : 0) : (pass == 1 ? 1 : 0); };
+    auto pass_a = [&](int pass) { return (p.npass == 3 && pass == 1) ? 1 : ((p.lo8 && pass == 1) ? 2 : 0); };
+    auto pass_b = [&](int pass) { return (p.npass == 3) ? (pass == 2 ? 1 : 0) : (pass == 1 ? (p.lo8 ? 2 : 1) : 0); };
     // instruction descriptor: D = f32 (bit 4), A / B format bf16 = 1 or f16 = 0 (bits 7, 10), both K-major, N (bits 17..), M (bits 24..)
     constexpr uint32_t kFmtBits = F16 ? 0u : ((1u << 7) | (1u << 10));
 
@@ -237,6 +247,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
         if constexpr (PAIR) umma_bf16_2sm(d, da, db, idesc, acc);
         else umma_bf16(d, da, db, idesc, acc);
     };
+    // e4m3 pass: same descriptors, same instruction-descriptor value with the format bits 0 (= E4M3), kind::f8f6f4
+    auto mma8 = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+        if constexpr (PAIR) umma_f8_2sm(d, da, db, idesc & ~((7u << 7) | (7u << 10)), acc);
+        else umma_f8(d, da, db, idesc & ~((7u << 7) | (7u << 10)), acc);
+    };
     auto commit = [&](uint32_t bar) {
         if constexpr (PAIR) umma_commit_2sm(bar, (uint16_t)0x3);
         else umma_commit(bar);
@@ -254,8 +269,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (elect_one()) {
                     expect(bar_bres, (uint32_t)res_bytes);
                     for (int kbg = 0; kbg < p.nkb; ++kbg) {                  // resident layout: [plane][tap][channel block]
-                        const int plane = kbg / kb_per_pass;
-                        load_wgt(bar_bres, base + kbg * kBTile, (kbg - plane * kb_per_pass) * kBlockK, 0, plane);
+                        if (p.lo8 && kbg >= p.kb0)                              // e4m3 lo plane: 128 channels per block
+                            load_wgt(bar_bres, base + kbg * kBTile, (kbg - p.kb0) * 128, 0, 2);
+                        else {
+                            const int plane = kbg / kb_per_pass;
+                            load_wgt(bar_bres, base + kbg * kBTile, (kbg - plane * kb_per_pass) * kBlockK, 0, plane);
+                        }
                     }
                 }
                 __syncwarp();
@@ -267,12 +286,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 const int wt = m % p.tiles_w; m /= p.tiles_w;
                 const int ht = m % p.tiles_h;
                 const int bt = m / p.tiles_h;
-                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                // lo8: the fp16 halo tiles of pass 0, then the e4m3 halo tiles (128 channels each) of pass 1
+                const int a_tiles = p.cin_blocks + (p.lo8 ? p.cin_blocks1 : 0);
+                for (int t = 0; t < a_tiles; ++t) {
+                    const bool f8 = t >= p.cin_blocks;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     if (elect_one()) {
                         expect(bar_full + 8 * stage, (uint32_t)kHaloBoxBytes);
-                        load_act(&p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes, cb * kBlockK,
-                                 wt * p.BW - 1, ht * p.BH - 1, bt);
+                        load_act(f8 ? &p.tmH8 : &p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes,
+                                 f8 ? (t - p.cin_blocks) * 128 : t * kBlockK, wt * p.BW - 1, ht * p.BH - 1, bt);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -295,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 int pass = 0, kb = 0, tap = 0, cb = 0;
                 int dy = 0, dx = 0;
                 if (p.taps == 9) { dy = -1; dx = -1; }
+                int cbs = p.cin_blocks, kbpp = kb_per_pass, kmul = kBlockK;   // of the current pass (lo8: pass 1 differs)
                 const uint32_t b_off = kABytes + (p.cluster > 1 ? crank * (Cfg::kBBytes >> cshift) : 0);
                 const int b_row = n0 + (p.cluster > 1 ? crank * (BN >> cshift) : 0);
                 for (int kbg = 0; kbg < p.nkb; ++kbg) {
@@ -308,30 +331,31 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         if (elect_one()) {
                             const uint32_t lead_full = mapa_rank(bar_full + 8 * stage, 0);
                             if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)stage_pitch);
-                            tma_load_4d_2sm(ta, lead_full, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
-                            tma_load_2d_2sm(&p.tmBh[bsel], lead_full, sa + kABytes, kb * kBlockK, n0 + crank * (BN / 2));
+                            tma_load_4d_2sm(ta, lead_full, sa, cb * kmul, x0 + dx, y0 + dy, b0);
+                            tma_load_2d_2sm(&p.tmBh[bsel], lead_full, sa + kABytes, kb * kmul, n0 + crank * (BN / 2));
                         }
                     } else {
                       if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
-                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kBlockK, x0 + dx, y0 + dy, b0);
+                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kmul, x0 + dx, y0 + dy, b0);
                         if (p.cluster > 1)      // my slice of the weight tile, into every CTA of the cluster
-                            tma_load_2d_multicast(&p.tmBh[bsel], bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row, cmask);
+                            tma_load_2d_multicast(&p.tmBh[bsel], bar_full + 8 * stage, sa + b_off, kb * kmul, b_row, cmask);
                         else
-                            tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kb * kBlockK, b_row);
+                            tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kb * kmul, b_row);
                       }
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     ++kb;
-                    if (++cb == p.cin_blocks) {
+                    if (++cb == cbs) {
                         cb = 0;
                         ++tap;
                         if (p.taps == 9 && ++dx == 2) { dx = -1; ++dy; }
                     }
-                    if (kb == kb_per_pass) {
+                    if (kb == kbpp) {
                         kb = 0; tap = 0; cb = 0; ++pass;
                         if (p.taps == 9) { dy = -1; dx = -1; }
+                        if (p.lo8) { cbs = p.cin_blocks1; kbpp = p.taps * p.cin_blocks1; kmul = 128; }
                     }
                 }
             }
@@ -345,13 +369,18 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (skip_unit(unit)) continue;
                 int m, n0;
                 unit_tile(unit, m, n0);
-                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                const int a_tiles = p.cin_blocks + (p.lo8 ? p.cin_blocks1 : 0);
+                for (int t = 0; t < a_tiles; ++t) {
+                    const bool f8 = t >= p.cin_blocks;                        // lo8: pass-1 tiles come after all pass-0 tiles
+                    const int cb = f8 ? t - p.cin_blocks : t;
+                    const int planes = p.lo8 ? 1 : p.npass;
                     for (int tap = 0; tap < 9; ++tap) {
-                        for (int plane = 0; plane < p.npass; ++plane) {       // fp16x2: the hi and the lo weight tile of this tap
+                        for (int plane = 0; plane < planes; ++plane) {        // fp16 lo pass: the hi and the lo weight tile of this tap
                             mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
                             if (elect_one()) {
                                 expect(bar_bfull + 8 * bs, (uint32_t)kBTile);
-                                load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (tap * p.cin_blocks + cb) * kBlockK, n0, plane);
+                                if (f8) load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (tap * p.cin_blocks1 + cb) * 128, n0, 2);
+                                else load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (tap * p.cin_blocks + cb) * kBlockK, n0, plane);
                             }
                             __syncwarp();
                             if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
@@ -379,34 +408,43 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             // of ONE descriptor (fully unrolled), and with resident weights the 36 MMAs of a channel block are
             // issued from a single elected region.  (The first version rebuilt descriptors and re-elected per tap
             // in a rolled loop: ~500 cycles of issue overhead per tap, 4x the MMA time at N = 64.)
-            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            const int a_tiles = p.cin_blocks + (p.lo8 ? p.cin_blocks1 : 0);
+            for (int t = 0; t < a_tiles; ++t) {
+                // lo8: tiles t >= cin_blocks are the e4m3 pass (128 channels per tile, one weight plane, f8f6f4 MMAs)
+                const bool f8 = t >= p.cin_blocks;
+                const int cb = f8 ? t - p.cin_blocks : t;
+                const int cbs = f8 ? p.cin_blocks1 : p.cin_blocks;
+                const int planes = p.lo8 ? 1 : p.npass;
+                const int slen = f8 ? p.seg_len1 : p.seg_len;
                 if (seg_left == 0) {                                        // open the next accumulation segment
                     as = gs % Cfg::kAcc;
                     mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);
                     tc_fence_after();
                     tmem_d = tmem_base + as * BN;
-                    seg_left = p.seg_len;
+                    seg_left = slen;
                     ++gs;
                 }
-                const int first = (seg_left == p.seg_len) ? 0 : 1;          // 0: this channel block starts the chain
+                const int first = (seg_left == slen) ? 0 : 1;               // 0: this channel block starts the chain
                 mbar_wait(bar_full + 8 * stage, phase, p.err_flag);         // halo tile landed
                 tc_fence_after();
                 const uint64_t da0 = make_halo_desc(stage_base + stage * kHaloBytes);
                 if (p.resb) {
-                    const uint32_t bstep = (uint32_t)(p.cin_blocks * kBTile) >> 4;   // next tap, same channel block
+                    const uint32_t bstep = (uint32_t)(cbs * kBTile) >> 4;   // next tap, same channel block
                     if (elect_one()) {
                         // (tap, plane) order like the weight-ring path below: a layer's accumulation order — and with it
                         // every bit of its output — is the same whichever path the batch size selects
-                        const uint64_t db0 = make_sw128_desc(base + cb * kBTile);
-                        const uint32_t pstep = (uint32_t)(kb_per_pass * kBTile) >> 4;    // hi plane -> lo plane (fp16x2)
+                        const uint64_t db0 = make_sw128_desc(base + ((f8 ? p.kb0 : 0) + cb) * kBTile);
+                        const uint32_t pstep = (uint32_t)(kb_per_pass * kBTile) >> 4;    // hi plane -> lo plane (fp16 lo pass)
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
-                            for (int plane = 0; plane < p.npass; ++plane) {
+                            for (int plane = 0; plane < planes; ++plane) {
                                 const uint64_t db = db0 + (uint64_t)(tap * bstep + plane * pstep);
 #pragma unroll
-                                for (int k = 0; k < kBlockK / 16; ++k)
-                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                for (int k = 0; k < kBlockK / 16; ++k) {
+                                    if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                    else mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                }
                             }
                         }
                         commit(bar_empty + 8 * stage);                 // halo tile free again
@@ -416,16 +454,18 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);
-                        for (int plane = 0; plane < p.npass; ++plane) {
+                        for (int plane = 0; plane < planes; ++plane) {
                             mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
                             tc_fence_after();
                             const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
                             if (elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < kBlockK / 16; ++k)
-                                    mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                for (int k = 0; k < kBlockK / 16; ++k) {
+                                    if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                    else mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                }
                                 commit(bar_bempty + 8 * bs);
-                                if (tap == 8 && plane == p.npass - 1) commit(bar_empty + 8 * stage);
+                                if (tap == 8 && plane == planes - 1) commit(bar_empty + 8 * stage);
                             }
                             __syncwarp();
                             if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
@@ -433,7 +473,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     }
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                if (--seg_left == 0 || cb == p.cin_blocks - 1) {            // segment complete -> epilogue adds it in
+                // segment complete (also at the pass boundary and at the end of the tile) -> epilogue adds it in
+                if (--seg_left == 0 || t == a_tiles - 1 || (p.lo8 && t == p.cin_blocks - 1)) {
                     seg_left = 0;
                     if (elect_one()) commit(bar_tfull + 8 * as);
                     __syncwarp();
@@ -450,9 +491,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int gs = 0;
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
                 if (skip_unit(unit)) continue;
-                for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
+                for (int k0 = 0, k1 = 0; k0 < p.nkb; k0 = k1, ++gs) {       // one accumulation chain per segment
                     const int as = gs % Cfg::kAcc;
-                    const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
+                    {   // lo8: segments end at the pass boundary kb0; pass 1 has its own segment length
+                        const bool in1 = p.lo8 && k0 >= p.kb0;
+                        const int lim = (p.lo8 && !in1) ? p.kb0 : p.nkb;
+                        k1 = k0 + (in1 ? p.seg_len1 : p.seg_len);
+                        if (k1 > lim) k1 = lim;
+                    }
                     mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);   // both CTAs' epilogues drained it
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
@@ -463,9 +509,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         const uint64_t da = make_sw128_desc(sa);
                         const uint64_t db = make_sw128_desc(sa + kABytes);
                         if (elect_one()) {
+                            const bool f8 = p.lo8 && kb >= p.kb0;
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k)
-                                umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                                else umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                            }
                             umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)0x3);   // stage free again, in both CTAs
                         }
                         __syncwarp();
@@ -486,9 +535,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             int gs = 0;
             for (int unit = unit0; unit < p.num_units; unit += ustep) {
                 if (skip_unit(unit)) continue;
-                for (int k0 = 0; k0 < p.nkb; k0 += p.seg_len, ++gs) {       // one accumulation chain per segment
+                for (int k0 = 0, k1 = 0; k0 < p.nkb; k0 = k1, ++gs) {       // one accumulation chain per segment
                     const int as = gs % Cfg::kAcc;
-                    const int k1 = (k0 + p.seg_len < p.nkb) ? k0 + p.seg_len : p.nkb;
+                    {   // lo8: segments end at the pass boundary kb0; pass 1 has its own segment length
+                        const bool in1 = p.lo8 && k0 >= p.kb0;
+                        const int lim = (p.lo8 && !in1) ? p.kb0 : p.nkb;
+                        k1 = k0 + (in1 ? p.seg_len1 : p.seg_len);
+                        if (k1 > lim) k1 = lim;
+                    }
                     mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
@@ -499,10 +553,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         const uint64_t da = make_sw128_desc(sa);
                         const uint64_t db = make_sw128_desc(sa + kABytes);
                         if (elect_one()) {
+                            const bool f8 = p.lo8 && kb >= p.kb0;
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                                if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                                else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
                             }
                             // frees the smem stage when the MMAs retire — in cluster mode on BOTH CTAs: the peer's
                             // producer multicasts into this stage too and must see it released
@@ -567,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 #pragma unroll 1
             for (int seg = 0; seg < p.nseg; ++seg, ++gs) {
                 const int as = gs % Cfg::kAcc;
+                const float sc = (seg >= p.nseg0) ? p.lo_scale : 1.0f;
                 mbar_wait(bar_tfull + 8 * as, ((uint32_t)gs / Cfg::kAcc) & 1u, p.err_flag);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN + grp * 32;
@@ -575,8 +632,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + ci * 64, r);
                     tmem_ld_wait();
+                    // (pass-1 segments of the e4m3 lo pass carry the factor 2^s of their weights; sc = 1 otherwise)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) run[ci][j] = __fmaf_rn(__uint_as_float(r[j]), sc, run[ci][j]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -654,6 +712,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             hi.x = pack_act2<F16>(g8[0], g8[1]); hi.y = pack_act2<F16>(g8[2], g8[3]);
                             hi.z = pack_act2<F16>(g8[4], g8[5]); hi.w = pack_act2<F16>(g8[6], g8[7]);
                             *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
+                            if (p.out8)
+                                *reinterpret_cast<uint2*>(p.out8 + o) = make_uint2(pack4_e4m3(g8[0], g8[1], g8[2], g8[3]),
+                                                                                   pack4_e4m3(g8[4], g8[5], g8[6], g8[7]));
                             if (!F16 && p.out_lo) {
                                 uint4 lo;
                                 lo.x = pack_bf16x2(g8[0] - bf16_round(g8[0]), g8[1] - bf16_round(g8[1]));
@@ -685,6 +746,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         }
                         st_global_256(p.out_hi + o, hi[0], hi[1]);          // 64 contiguous bytes per lane: two full sectors
                         st_global_256(p.out_hi + o + 16, hi[2], hi[3]);
+                        if (p.out8) {
+                            uint4 q0, q1;
+                            q0.x = pack4_e4m3(v[0], v[1], v[2], v[3]);     q0.y = pack4_e4m3(v[4], v[5], v[6], v[7]);
+                            q0.z = pack4_e4m3(v[8], v[9], v[10], v[11]);   q0.w = pack4_e4m3(v[12], v[13], v[14], v[15]);
+                            q1.x = pack4_e4m3(v[16], v[17], v[18], v[19]); q1.y = pack4_e4m3(v[20], v[21], v[22], v[23]);
+                            q1.z = pack4_e4m3(v[24], v[25], v[26], v[27]); q1.w = pack4_e4m3(v[28], v[29], v[30], v[31]);
+                            st_global_256(p.out8 + o, q0, q1);
+                        }
                         if (!F16 && p.out_lo) {
                             uint4 lo[4];
 #pragma unroll
@@ -748,14 +817,17 @@ int gemm_init(fadb_handle* h) {
 }
 
 // rs = row stride in elements (0 = C: rows are dense)
-static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB, bool f16,
+// kind: 0 = bf16, 1 = fp16, 2 = e4m3 bytes (128 channels per 128-byte box row instead of 64)
+static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H, int B, int BW, int BH, int BB, int kind,
                           long long rs = 0) {
     if (rs <= 0) rs = C;
+    const cuuint64_t es = kind == 2 ? 1 : 2;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)W * rs * 2, (cuuint64_t)H * W * rs * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BB};
+    cuuint64_t strides[3] = {(cuuint64_t)rs * es, (cuuint64_t)W * rs * es, (cuuint64_t)H * W * rs * es};
+    cuuint32_t box[4] = {(cuuint32_t)(kind == 2 ? 128 : kBlockK), (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+    CUresult r = g_encode(tm, kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                              : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4,
                           const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -767,13 +839,15 @@ static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H,
     return FADB_OK;
 }
 
-static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN, bool f16, long long rs = 0) {
+static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN, int kind, long long rs = 0) {
     if (rs <= 0) rs = K;
+    const cuuint64_t es = kind == 2 ? 1 : 2;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)rs * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint64_t strides[1] = {(cuuint64_t)rs * es};
+    cuuint32_t box[2] = {(cuuint32_t)(kind == 2 ? 128 : kBlockK), (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+    CUresult r = g_encode(tm, kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                              : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2,
                           const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -845,6 +919,9 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    // fp16x2: the low-order weight pass in e4m3 (twice the MMA rate, half the operand bytes) where the layer has whole
+    // 128-channel blocks and both e4m3 operands exist
+    const bool lo8 = npass == 2 && !io.syrk && h->lo_fp8 && io.in8 && L.w8 && io.Cin % 128 == 0;
     FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16, io.row_stride));
     if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1, f16));
     else p.tmH = p.tmA[0];
@@ -853,7 +930,17 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.tmA[1] = p.tmA[0];
     p.tmB[1] = p.tmB[0];
     if (npass == 3) FADB_CHECK(encode_act_map(&p.tmA[1], io.in_lo, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16, io.row_stride));
-    if (npass >= 2) FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN, f16, io.row_stride));
+    if (npass >= 2 && !lo8) FADB_CHECK(encode_weight_map(&p.tmB[1], L.w_lo, L.K, L.N, BN, f16, io.row_stride));
+    p.tmA[2] = p.tmA[0];
+    p.tmB[2] = p.tmB[0];
+    p.tmH8 = p.tmH;
+    if (lo8) {
+        FADB_CHECK(encode_act_map(&p.tmA[2], io.in8, io.Cin, io.W, io.H, io.B, BW, BH, BB, 2));
+        if (halo) FADB_CHECK(encode_act_map(&p.tmH8, io.in8, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1, 2));
+        FADB_CHECK(encode_weight_map(&p.tmB[2], L.w8, L.K, L.N, BN, 2));
+    }
+    p.lo8 = lo8 ? 1 : 0;
+    p.lo_scale = lo8 ? L.lo_scale : 1.f;
     p.W = io.W; p.H = io.H; p.B = io.B;
     p.BW = BW; p.BH = BH; p.BB = BB;
     p.tiles_w = (io.W + BW - 1) / BW;
@@ -877,6 +964,7 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.upper_only = io.syrk;
     p.out_f32 = io.out_f32;
     p.out_f64 = io.out_f64;
+    p.out8 = (h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && !io.out_f32 && L.N % 128 == 0) ? io.out8 : nullptr;
     p.err_flag = h->err_flag;
     FADB_REQUIRE(p.out_f32 || p.out_hi || p.out_f64, "layer has no output buffer");
 
@@ -947,10 +1035,12 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
             if (pair_mode) { pp.twocta = 1; apply(pair); smem = pair.smem; }
             g = cs * (h->sm_count / cs);
             if (encode_weight_map(&pp.tmBh[0], L.w_hi, L.K, L.N, BN / cs, f16, io.row_stride) != FADB_OK ||
-                (npass >= 2 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16, io.row_stride) != FADB_OK)) {
+                (npass >= 2 && !pp.lo8 && encode_weight_map(&pp.tmBh[1], L.w_lo, L.K, L.N, BN / cs, f16, io.row_stride) != FADB_OK) ||
+                (pp.lo8 && encode_weight_map(&pp.tmBh[2], L.w8, L.K, L.N, BN / cs, 2) != FADB_OK)) {
                 pp.cluster = 1; pp.num_units = pp.num_tiles; g = grid; pp.twocta = 0; apply(plain); smem = plain.smem;
             }
-            if (npass < 2) pp.tmBh[1] = pp.tmBh[0];
+            if (npass < 2 || pp.lo8) pp.tmBh[1] = pp.tmBh[0];
+            if (!pp.lo8) pp.tmBh[2] = pp.tmBh[0];
         }
         void (*kern)(GemmParams);
         void (*kern_pair)(GemmParams);
@@ -1023,15 +1113,33 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     };
     // accumulation segments (GemmParams::nseg): chains of at most kSegmentBlocks K blocks (64 MMAs); in halo mode a
     // segment is a whole number of channel blocks (9 * npass K blocks each)
-    p.nkb = npass * io.taps * p.cin_blocks;
+    p.kb0 = io.taps * p.cin_blocks;
+    p.cin_blocks1 = lo8 ? io.Cin / 128 : p.cin_blocks;
+    p.nkb = lo8 ? p.kb0 + io.taps * p.cin_blocks1 : npass * io.taps * p.cin_blocks;
+    auto split = [](int n, int kseg, int& nseg, int& len) {          // n K blocks into chains of <= kseg, evenly
+        nseg = (n + kseg - 1) / kseg;
+        len = (n + nseg - 1) / nseg;
+        nseg = (n + len - 1) / len;
+    };
     if (halo) {
-        p.seg_len = kSegmentBlocks / (9 * npass) > 0 ? kSegmentBlocks / (9 * npass) : 1;
-        p.nseg = (p.cin_blocks + p.seg_len - 1) / p.seg_len;
+        const int planes = lo8 ? 1 : npass;                          // weight planes multiplied per activation tile
+        p.seg_len = kSegmentBlocks / (9 * planes) > 0 ? kSegmentBlocks / (9 * planes) : 1;
+        p.nseg0 = (p.cin_blocks + p.seg_len - 1) / p.seg_len;
+        p.seg_len1 = 1;
+        p.nseg = p.nseg0 + (lo8 ? p.cin_blocks1 : 0);
+        if (!lo8) p.nseg0 = p.nseg;
     } else {
         const int kseg = io.seg_blocks > 0 ? io.seg_blocks : kSegmentBlocks;
-        p.nseg = (p.nkb + kseg - 1) / kseg;
-        p.seg_len = (p.nkb + p.nseg - 1) / p.nseg;
-        p.nseg = (p.nkb + p.seg_len - 1) / p.seg_len;
+        if (lo8) {
+            int n1 = 0;
+            split(p.kb0, kseg, p.nseg0, p.seg_len);
+            split(p.nkb - p.kb0, kseg, n1, p.seg_len1);
+            p.nseg = p.nseg0 + n1;
+        } else {
+            split(p.nkb, kseg, p.nseg, p.seg_len);
+            p.nseg0 = p.nseg;
+            p.seg_len1 = p.seg_len;
+        }
     }
     launch(p);
     FADB_CUDA_CHECK(launch_err);

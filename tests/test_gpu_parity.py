@@ -109,7 +109,8 @@ def test_tcgen05_layer_matches_conv2d(eng_bare, prec, case):
     ref = F.max_pool2d(ref, 2) if pool == 1 else (F.avg_pool2d(ref, 2) if pool == 2 else ref)
     ref = ref.permute(0, 2, 3, 1).numpy()
     assert out.shape == ref.shape
-    assert relerr(out, ref) < (1e-4 if prec == "bf16x3" else 2e-5)
+    # fp16x2 multiplies the low-order weight plane in e4m3 where Cin % 128 == 0 (a 2^-12 correction known to ~6 %)
+    assert relerr(out, ref) < (1e-4 if prec == "bf16x3" else (5e-5 if prec == "fp16x2" else 2e-5))
 
 
 PAIR_MODES = {
