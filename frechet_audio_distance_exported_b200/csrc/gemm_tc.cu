@@ -318,12 +318,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 int dy = 0, dx = 0;
                 if (p.taps == 9) { dy = -1; dx = -1; }
                 int cbs = p.cin_blocks, kbpp = kb_per_pass, kmul = kBlockK;   // of the current pass (lo8: pass 1 differs)
+                // everything that only changes with the pass is kept out of the per-K-block path (this loop paces the
+                // pipeline): tensor maps, and the K / channel coordinates as running sums
+                const CUtensorMap* ta = &p.tmA[0];
+                const CUtensorMap* tb = &p.tmB[0];
+                const CUtensorMap* tbh = &p.tmBh[0];
+                int ccoord = 0, kcoord = 0;
                 const uint32_t b_off = kABytes + (p.cluster > 1 ? crank * (Cfg::kBBytes >> cshift) : 0);
                 const int b_row = n0 + (p.cluster > 1 ? crank * (BN >> cshift) : 0);
                 for (int kbg = 0; kbg < p.nkb; ++kbg) {
-                    const CUtensorMap* ta = &p.tmA[pass_a(pass)];
-                    const int bsel = pass_b(pass);
-                    const CUtensorMap* tb = &p.tmB[bsel];
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     const uint32_t sa = stage_base + stage * stage_pitch;
                     if constexpr (PAIR) {
@@ -331,31 +334,38 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         if (elect_one()) {
                             const uint32_t lead_full = mapa_rank(bar_full + 8 * stage, 0);
                             if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)stage_pitch);
-                            tma_load_4d_2sm(ta, lead_full, sa, cb * kmul, x0 + dx, y0 + dy, b0);
-                            tma_load_2d_2sm(&p.tmBh[bsel], lead_full, sa + kABytes, kb * kmul, n0 + crank * (BN / 2));
+                            tma_load_4d_2sm(ta, lead_full, sa, ccoord, x0 + dx, y0 + dy, b0);
+                            tma_load_2d_2sm(tbh, lead_full, sa + kABytes, kcoord, n0 + crank * (BN / 2));
                         }
                     } else {
                       if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)stage_pitch);
-                        tma_load_4d(ta, bar_full + 8 * stage, sa, cb * kmul, x0 + dx, y0 + dy, b0);
+                        tma_load_4d(ta, bar_full + 8 * stage, sa, ccoord, x0 + dx, y0 + dy, b0);
                         if (p.cluster > 1)      // my slice of the weight tile, into every CTA of the cluster
-                            tma_load_2d_multicast(&p.tmBh[bsel], bar_full + 8 * stage, sa + b_off, kb * kmul, b_row, cmask);
+                            tma_load_2d_multicast(tbh, bar_full + 8 * stage, sa + b_off, kcoord, b_row, cmask);
                         else
-                            tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kb * kmul, b_row);
+                            tma_load_2d(tb, bar_full + 8 * stage, sa + b_off, kcoord, b_row);
                       }
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     ++kb;
+                    kcoord += kmul;
+                    ccoord += kmul;
                     if (++cb == cbs) {
                         cb = 0;
+                        ccoord = 0;
                         ++tap;
                         if (p.taps == 9 && ++dx == 2) { dx = -1; ++dy; }
                     }
                     if (kb == kbpp) {
                         kb = 0; tap = 0; cb = 0; ++pass;
+                        kcoord = 0; ccoord = 0;
                         if (p.taps == 9) { dy = -1; dx = -1; }
                         if (p.lo8) { cbs = p.cin_blocks1; kbpp = p.taps * p.cin_blocks1; kmul = 128; }
+                        ta = &p.tmA[pass_a(pass)];
+                        tb = &p.tmB[pass_b(pass)];
+                        tbh = &p.tmBh[pass_b(pass)];
                     }
                 }
             }
@@ -502,6 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);   // both CTAs' epilogues drained it
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
+                    const bool f8 = p.lo8 && k0 >= p.kb0;                    // whole segment: e4m3 pass or not
                     for (int kb = k0; kb < k1; ++kb) {
                         mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // both CTAs' TMA bytes landed
                         tc_fence_after();
@@ -509,11 +520,14 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         const uint64_t da = make_sw128_desc(sa);
                         const uint64_t db = make_sw128_desc(sa + kABytes);
                         if (elect_one()) {
-                            const bool f8 = p.lo8 && kb >= p.kb0;
+                            if (f8) {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k) {
-                                if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
-                                else umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)0x3);   // stage free again, in both CTAs
                         }
@@ -553,12 +567,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         const uint64_t da = make_sw128_desc(sa);
                         const uint64_t db = make_sw128_desc(sa + kABytes);
                         if (elect_one()) {
-                            const bool f8 = p.lo8 && kb >= p.kb0;
+                            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+                            if (p.lo8 && k0 >= p.kb0) {                 // whole segment: e4m3 pass
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k) {
-                                // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                                if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
-                                else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
                             }
                             // frees the smem stage when the MMAs retire — in cluster mode on BOTH CTAs: the peer's
                             // producer multicasts into this stage too and must see it released
