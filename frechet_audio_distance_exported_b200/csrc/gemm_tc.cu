@@ -438,50 +438,57 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 mbar_wait(bar_full + 8 * stage, phase, p.err_flag);         // halo tile landed
                 tc_fence_after();
                 const uint64_t da0 = make_halo_desc(stage_base + stage * kHaloBytes);
-                if (p.resb) {
-                    const uint32_t bstep = (uint32_t)(cbs * kBTile) >> 4;   // next tap, same channel block
-                    if (elect_one()) {
-                        // (tap, plane) order like the weight-ring path below: a layer's accumulation order — and with it
-                        // every bit of its output — is the same whichever path the batch size selects
-                        const uint64_t db0 = make_sw128_desc(base + ((f8 ? p.kb0 : 0) + cb) * kBTile);
-                        const uint32_t pstep = (uint32_t)(kb_per_pass * kBTile) >> 4;    // hi plane -> lo plane (fp16 lo pass)
+                // The MMA issue sequence of a tile is kept free of data-dependent branches (the e4m3 / fp16 choice is made
+                // once per tile, outside the unrolled loops): a branch between two tcgen05.mma issues costs more than the MMA.
+                auto issue_tile = [&](auto f8tag) {
+                    constexpr bool F8 = decltype(f8tag)::value;
+                    if (p.resb) {
+                        const uint32_t bstep = (uint32_t)(cbs * kBTile) >> 4;   // next tap, same channel block
+                        if (elect_one()) {
+                            // (tap, plane) order like the weight-ring path below: a layer's accumulation order — and with
+                            // it every bit of its output — is the same whichever path the batch size selects
+                            const uint64_t db0 = make_sw128_desc(base + ((F8 ? p.kb0 : 0) + cb) * kBTile);
+                            const uint32_t pstep = (uint32_t)(kb_per_pass * kBTile) >> 4;    // hi plane -> lo plane (fp16 lo pass)
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
+                                for (int plane = 0; plane < planes; ++plane) {
+                                    const uint64_t db = db0 + (uint64_t)(tap * bstep + plane * pstep);
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k) {
+                                        if constexpr (F8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                        else mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                    }
+                                }
+                            }
+                            commit(bar_empty + 8 * stage);                 // halo tile free again
+                        }
+                        __syncwarp();
+                    } else {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);   // (ky*10+kx)*128 B >> 4
+                            const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);
                             for (int plane = 0; plane < planes; ++plane) {
-                                const uint64_t db = db0 + (uint64_t)(tap * bstep + plane * pstep);
+                                mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
+                                tc_fence_after();
+                                const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
+                                if (elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < kBlockK / 16; ++k) {
-                                    if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
-                                    else mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                    for (int k = 0; k < kBlockK / 16; ++k) {
+                                        if constexpr (F8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                        else mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
+                                    }
+                                    commit(bar_bempty + 8 * bs);
+                                    if (tap == 8 && plane == planes - 1) commit(bar_empty + 8 * stage);
                                 }
+                                __syncwarp();
+                                if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
                             }
                         }
-                        commit(bar_empty + 8 * stage);                 // halo tile free again
                     }
-                    __syncwarp();
-                } else {
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint64_t da = da0 + (uint64_t)(((tap / 3) * kHaloW + (tap % 3)) * 8);
-                        for (int plane = 0; plane < planes; ++plane) {
-                            mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
-                            tc_fence_after();
-                            const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < kBlockK / 16; ++k) {
-                                    if (f8) mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
-                                    else mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | tap | k | plane) != 0 ? 1u : 0u);
-                                }
-                                commit(bar_bempty + 8 * bs);
-                                if (tap == 8 && plane == planes - 1) commit(bar_empty + 8 * stage);
-                            }
-                            __syncwarp();
-                            if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
-                        }
-                    }
-                }
+                };
+                if (f8) issue_tile(std::true_type{});
+                else issue_tile(std::false_type{});
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 // segment complete (also at the pass boundary and at the end of the tile) -> epilogue adds it in
                 if (--seg_left == 0 || t == a_tiles - 1 || (p.lo8 && t == p.cin_blocks - 1)) {
