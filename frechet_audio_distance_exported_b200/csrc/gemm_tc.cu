@@ -129,7 +129,9 @@ struct GemmCfg {
 // SYRK = the statistics variant (stats.cu): the finished tile (fp32 segment sums of one short row chunk) is ADDED to the
 // fp64 second-moment matrix; no bias / activation / pooling.  (Adding every segment in fp64 registers was measured:
 // the 64 F2F conversions per thread and segment cost more than the MMAs of a 16-MMA segment.)
-template <int BN, bool PAIR, bool F16, bool SYRK = false>
+// LO8 = fp16x2 with the e4m3 low-order pass (GemmParams::lo8).  A template parameter so that the single-pass and bf16x3
+// instantiations carry none of its branches: with a run-time flag alone they ran 8 % (VGGish) to 14 % (CNN14) slower.
+template <int BN, bool PAIR, bool F16, bool SYRK = false, bool LO8 = false>
 __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BN>;
     const int kStages = p.stages;
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 
     const int kb_per_pass = p.taps * p.cin_blocks;
     // which activation / weight plane a pass multiplies: npass 1: (0,0); 2: (0,0),(0,1); 3: (0,0),(1,0),(0,1)
-    auto pass_a = [&](int pass) { return (p.npass == 3 && pass == 1) ? 1 : ((p.lo8 && pass == 1) ? 2 : 0); };
-    auto pass_b = [&](int pass) { return (p.npass == 3) ? (pass == 2 ? 1 : 0) : (pass == 1 ? (p.lo8 ? 2 : 1) : 0); };
+    auto pass_a = [&](int pass) { return (p.npass == 3 && pass == 1) ? 1 : ((LO8 && pass == 1) ? 2 : 0); };
+    auto pass_b = [&](int pass) { return (p.npass == 3) ? (pass == 2 ? 1 : 0) : (pass == 1 ? (LO8 ? 2 : 1) : 0); };
     // instruction descriptor: D = f32 (bit 4), A / B format bf16 = 1 or f16 = 0 (bits 7, 10), both K-major, N (bits 17..), M (bits 24..)
     constexpr uint32_t kFmtBits = F16 ? 0u : ((1u << 7) | (1u << 10));
 
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (elect_one()) {
                     expect(bar_bres, (uint32_t)res_bytes);
                     for (int kbg = 0; kbg < p.nkb; ++kbg) {                  // resident layout: [plane][tap][channel block]
-                        if (p.lo8 && kbg >= p.kb0)                              // e4m3 lo plane: 128 channels per block
+                        if (LO8 && kbg >= p.kb0)                              // e4m3 lo plane: 128 channels per block
                             load_wgt(bar_bres, base + kbg * kBTile, (kbg - p.kb0) * 128, 0, 2);
                         else {
                             const int plane = kbg / kb_per_pass;
@@ -287,9 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 const int ht = m % p.tiles_h;
                 const int bt = m / p.tiles_h;
                 // lo8: the fp16 halo tiles of pass 0, then the e4m3 halo tiles (128 channels each) of pass 1
-                const int a_tiles = p.cin_blocks + (p.lo8 ? p.cin_blocks1 : 0);
+                const int a_tiles = p.cin_blocks + (LO8 ? p.cin_blocks1 : 0);
                 for (int t = 0; t < a_tiles; ++t) {
-                    const bool f8 = t >= p.cin_blocks;
+                    const bool f8 = LO8 && t >= p.cin_blocks;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     if (elect_one()) {
                         expect(bar_full + 8 * stage, (uint32_t)kHaloBoxBytes);
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         kb = 0; tap = 0; cb = 0; ++pass;
                         kcoord = 0; ccoord = 0;
                         if (p.taps == 9) { dy = -1; dx = -1; }
-                        if (p.lo8) { cbs = p.cin_blocks1; kbpp = p.taps * p.cin_blocks1; kmul = 128; }
+                        if (LO8) { cbs = p.cin_blocks1; kbpp = p.taps * p.cin_blocks1; kmul = 128; }
                         ta = &p.tmA[pass_a(pass)];
                         tb = &p.tmB[pass_b(pass)];
                         tbh = &p.tmBh[pass_b(pass)];
@@ -379,11 +381,11 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (skip_unit(unit)) continue;
                 int m, n0;
                 unit_tile(unit, m, n0);
-                const int a_tiles = p.cin_blocks + (p.lo8 ? p.cin_blocks1 : 0);
+                const int a_tiles = p.cin_blocks + (LO8 ? p.cin_blocks1 : 0);
                 for (int t = 0; t < a_tiles; ++t) {
-                    const bool f8 = t >= p.cin_blocks;                        // lo8: pass-1 tiles come after all pass-0 tiles
+                    const bool f8 = LO8 && t >= p.cin_blocks;                        // lo8: pass-1 tiles come after all pass-0 tiles
                     const int cb = f8 ? t - p.cin_blocks : t;
-                    const int planes = p.lo8 ? 1 : p.npass;
+                    const int planes = LO8 ? 1 : p.npass;
                     for (int tap = 0; tap < 9; ++tap) {
                         for (int plane = 0; plane < planes; ++plane) {        // fp16 lo pass: the hi and the lo weight tile of this tap
                             mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
@@ -418,13 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             // of ONE descriptor (fully unrolled), and with resident weights the 36 MMAs of a channel block are
             // issued from a single elected region.  (The first version rebuilt descriptors and re-elected per tap
             // in a rolled loop: ~500 cycles of issue overhead per tap, 4x the MMA time at N = 64.)
-            const int a_tiles = p.cin_blocks + (p.lo8 ? p.cin_blocks1 : 0);
+            const int a_tiles = p.cin_blocks + (LO8 ? p.cin_blocks1 : 0);
             for (int t = 0; t < a_tiles; ++t) {
                 // lo8: tiles t >= cin_blocks are the e4m3 pass (128 channels per tile, one weight plane, f8f6f4 MMAs)
-                const bool f8 = t >= p.cin_blocks;
+                const bool f8 = LO8 && t >= p.cin_blocks;
                 const int cb = f8 ? t - p.cin_blocks : t;
                 const int cbs = f8 ? p.cin_blocks1 : p.cin_blocks;
-                const int planes = p.lo8 ? 1 : p.npass;
+                const int planes = LO8 ? 1 : p.npass;
                 const int slen = f8 ? p.seg_len1 : p.seg_len;
                 if (seg_left == 0) {                                        // open the next accumulation segment
                     as = gs % Cfg::kAcc;
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 else issue_tile(std::false_type{});
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 // segment complete (also at the pass boundary and at the end of the tile) -> epilogue adds it in
-                if (--seg_left == 0 || t == a_tiles - 1 || (p.lo8 && t == p.cin_blocks - 1)) {
+                if (--seg_left == 0 || t == a_tiles - 1 || (LO8 && t == p.cin_blocks - 1)) {
                     seg_left = 0;
                     if (elect_one()) commit(bar_tfull + 8 * as);
                     __syncwarp();
@@ -511,15 +513,15 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 for (int k0 = 0, k1 = 0; k0 < p.nkb; k0 = k1, ++gs) {       // one accumulation chain per segment
                     const int as = gs % Cfg::kAcc;
                     {   // lo8: segments end at the pass boundary kb0; pass 1 has its own segment length
-                        const bool in1 = p.lo8 && k0 >= p.kb0;
-                        const int lim = (p.lo8 && !in1) ? p.kb0 : p.nkb;
+                        const bool in1 = LO8 && k0 >= p.kb0;
+                        const int lim = (LO8 && !in1) ? p.kb0 : p.nkb;
                         k1 = k0 + (in1 ? p.seg_len1 : p.seg_len);
                         if (k1 > lim) k1 = lim;
                     }
                     mbar_wait(bar_tempty + 8 * as, (((uint32_t)gs / Cfg::kAcc) & 1u) ^ 1u, p.err_flag);   // both CTAs' epilogues drained it
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
-                    const bool f8 = p.lo8 && k0 >= p.kb0;                    // whole segment: e4m3 pass or not
+                    const bool f8 = LO8 && k0 >= p.kb0;                    // whole segment: e4m3 pass or not
                     for (int kb = k0; kb < k1; ++kb) {
                         mbar_wait(bar_full + 8 * stage, phase, p.err_flag);     // both CTAs' TMA bytes landed
                         tc_fence_after();
@@ -559,8 +561,8 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 for (int k0 = 0, k1 = 0; k0 < p.nkb; k0 = k1, ++gs) {       // one accumulation chain per segment
                     const int as = gs % Cfg::kAcc;
                     {   // lo8: segments end at the pass boundary kb0; pass 1 has its own segment length
-                        const bool in1 = p.lo8 && k0 >= p.kb0;
-                        const int lim = (p.lo8 && !in1) ? p.kb0 : p.nkb;
+                        const bool in1 = LO8 && k0 >= p.kb0;
+                        const int lim = (LO8 && !in1) ? p.kb0 : p.nkb;
                         k1 = k0 + (in1 ? p.seg_len1 : p.seg_len);
                         if (k1 > lim) k1 = lim;
                     }
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         const uint64_t db = make_sw128_desc(sa + kABytes);
                         if (elect_one()) {
                             // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                            if (p.lo8 && k0 >= p.kb0) {                 // whole segment: e4m3 pass
+                            if (LO8 && k0 >= p.kb0) {                 // whole segment: e4m3 pass
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)
                                     mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > k0 || k > 0) ? 1u : 0u);
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
 #pragma unroll 1
             for (int seg = 0; seg < p.nseg; ++seg, ++gs) {
                 const int as = gs % Cfg::kAcc;
-                const float sc = (seg >= p.nseg0) ? p.lo_scale : 1.0f;
+                const float sc = (LO8 && seg >= p.nseg0) ? p.lo_scale : 1.0f;
                 mbar_wait(bar_tfull + 8 * as, ((uint32_t)gs / Cfg::kAcc) & 1u, p.err_flag);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + as * BN + grp * 32;
@@ -658,7 +660,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     tmem_ld_wait();
                     // (pass-1 segments of the e4m3 lo pass carry the factor 2^s of their weights; sc = 1 otherwise)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) run[ci][j] = __fmaf_rn(__uint_as_float(r[j]), sc, run[ci][j]);
+                    for (int j = 0; j < 32; ++j) {
+                        if constexpr (LO8) run[ci][j] = __fmaf_rn(__uint_as_float(r[j]), sc, run[ci][j]);
+                        else run[ci][j] = __fadd_rn(run[ci][j], __uint_as_float(r[j]));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -736,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             hi.x = pack_act2<F16>(g8[0], g8[1]); hi.y = pack_act2<F16>(g8[2], g8[3]);
                             hi.z = pack_act2<F16>(g8[4], g8[5]); hi.w = pack_act2<F16>(g8[6], g8[7]);
                             *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
-                            if (p.out8)
+                            if (F16 && p.out8)
                                 *reinterpret_cast<uint2*>(p.out8 + o) = make_uint2(pack4_e4m3(g8[0], g8[1], g8[2], g8[3]),
                                                                                    pack4_e4m3(g8[4], g8[5], g8[6], g8[7]));
                             if (!F16 && p.out_lo) {
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         }
                         st_global_256(p.out_hi + o, hi[0], hi[1]);          // 64 contiguous bytes per lane: two full sectors
                         st_global_256(p.out_hi + o + 16, hi[2], hi[3]);
-                        if (p.out8) {
+                        if (F16 && p.out8) {
                             uint4 q0, q1;
                             q0.x = pack4_e4m3(v[0], v[1], v[2], v[3]);     q0.y = pack4_e4m3(v[4], v[5], v[6], v[7]);
                             q0.z = pack4_e4m3(v[8], v[9], v[10], v[11]);   q0.w = pack4_e4m3(v[12], v[13], v[14], v[15]);
@@ -835,7 +840,10 @@ int gemm_init(fadb_handle* h) {
                                   fadb_gemm_tc_kernel<64, false, true>, fadb_gemm_tc_kernel<128, false, true>,
                                   fadb_gemm_tc_kernel<256, false, true>, fadb_gemm_tc_kernel<64, true, true>,
                                   fadb_gemm_tc_kernel<128, true, true>, fadb_gemm_tc_kernel<256, true, true>,
-                                  fadb_gemm_tc_kernel<128, false, true, true>, fadb_gemm_tc_kernel<128, true, true, true>})
+                                  fadb_gemm_tc_kernel<128, false, true, true>, fadb_gemm_tc_kernel<128, true, true, true>,
+                                  fadb_gemm_tc_kernel<64, false, true, false, true>, fadb_gemm_tc_kernel<128, false, true, false, true>,
+                                  fadb_gemm_tc_kernel<256, false, true, false, true>, fadb_gemm_tc_kernel<64, true, true, false, true>,
+                                  fadb_gemm_tc_kernel<128, true, true, false, true>, fadb_gemm_tc_kernel<256, true, true, false, true>})
         FADB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kMaxSmemBytes));
     return FADB_OK;
 }
@@ -1082,6 +1090,14 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
         if (io.syrk) {
             kern = fadb_gemm_tc_kernel<128, false, true, true>;
             kern_pair = fadb_gemm_tc_kernel<128, true, true, true>;
+        }
+        if (pp.lo8) {
+            kern = (BN == 256) ? fadb_gemm_tc_kernel<256, false, true, false, true>
+                               : (BN == 128 ? fadb_gemm_tc_kernel<128, false, true, false, true>
+                                            : fadb_gemm_tc_kernel<64, false, true, false, true>);
+            kern_pair = (BN == 256) ? fadb_gemm_tc_kernel<256, true, true, false, true>
+                                    : (BN == 128 ? fadb_gemm_tc_kernel<128, true, true, false, true>
+                                                 : fadb_gemm_tc_kernel<64, true, true, false, true>);
         }
         void (*kern_plain)(GemmParams) = kern;
         if (pp.twocta) kern = kern_pair;
