@@ -27,6 +27,7 @@ SYMBOLS = [
     ("fadb_set_precision", C.c_int, [_vp, C.c_int]),
     ("fadb_set_max_batch", C.c_int, [_vp, C.c_int]),
     ("fadb_set_tensor_syrk", C.c_int, [_vp, C.c_int]),
+    ("fadb_set_clap_quantize", C.c_int, [_vp, C.c_int]),
     ("fadb_weights_begin", C.c_int, [_vp, C.c_int]),
     ("fadb_weights_tensor", C.c_int, [_vp, C.c_char_p, _fp, C.POINTER(C.c_int64), C.c_int]),
     ("fadb_weights_commit", C.c_int, [_vp]),

@@ -558,6 +558,12 @@ int fadb_set_tensor_syrk(fadb_handle* h, int on) {
     return FADB_OK;
 }
 
+int fadb_set_clap_quantize(fadb_handle* h, int on) {
+    if (!h) { set_error("fadb_set_clap_quantize: NULL handle"); return FADB_E_INVALID; }
+    h->clap_quantize = on ? 1 : 0;
+    return FADB_OK;
+}
+
 int fadb_set_max_batch(fadb_handle* h, int max_items) {
     if (!h || max_items < 1 || max_items > 65535) { set_error("max_batch must be in [1, 65535]"); return FADB_E_INVALID; }
     h->max_batch = max_items;

@@ -151,6 +151,7 @@ struct fadb_handle {
     fadb::DevBuf ws_frechet;    // fp64 workspace of fadb_frechet
     fadb::DevBuf ws_stats;      // fp64 workspace of fadb_fad_from_pcm_host
     fadb::DevBuf ws_syrk;       // tensor-core syrk: transposed split-fp16 planes of one row chunk + its fp32 product
+    int clap_quantize = 1;      // CLAP front end applies clap.py:70-72's int16 truncation (fadb_set_clap_quantize)
     int tc_syrk = 0;            // 1: second moments of >= 8192 rows at d >= 512 on the tensor cores (fadb_set_tensor_syrk /
                                 // FADB_TC_SYRK): ~8x faster, covariance accurate to ~1e-6 instead of 1e-14 — OFF by default
                                 // because FAD between two SIMILAR sets amplifies that error by tr(S) / FAD

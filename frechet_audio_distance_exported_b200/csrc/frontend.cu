@@ -847,7 +847,7 @@ int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int6
     p.win_len = t.win_len;
     p.centered = (model != FADB_MODEL_VGGISH);
     p.power_db = (model != FADB_MODEL_VGGISH);
-    p.quantize = (model == FADB_MODEL_CLAP);
+    p.quantize = (model == FADB_MODEL_CLAP) && h->clap_quantize;
     p.tw = t.tw; p.win = t.win;
     p.band_start = t.band_start; p.band_len = t.band_len;
     p.band_wt = t.band_wt; p.wt_rows = t.wt_rows; p.wt_off1 = t.wt_off1;

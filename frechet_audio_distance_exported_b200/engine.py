@@ -74,6 +74,11 @@ class Engine:
         instead of fp64-exact.  Off by default (include/fadb.h: fadb_set_tensor_syrk)."""
         check(self.lib.fadb_set_tensor_syrk(self.h, int(bool(on))))
 
+    def set_clap_quantize(self, on: bool) -> None:
+        """CLAP front end: apply clap.py:70-72's int16 truncation to the samples (default) or take them as they are
+        (already quantised at the source rate by the caller, include/fadb.h: fadb_set_clap_quantize)."""
+        check(self.lib.fadb_set_clap_quantize(self.h, int(bool(on))))
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """Hand the reference modules' state_dict (VGGishCore / PANNCore key names) to the packer."""
         check(self.lib.fadb_weights_begin(self.h, self.model_id))

@@ -25,6 +25,7 @@ from .resample import resample
 from .stream import HostRing
 
 CLAP_TIME_FRAMES = 1001                       # fad.py:38
+_CLAP_MAX_SAMPLES = 480000                    # fad.py:355 (CLAP_MAX_SECONDS * CLAP_SAMPLE_RATE)
 
 # fad.py:109-117
 VALID_MODELS = {
@@ -224,6 +225,16 @@ class FrechetAudioDistance:
             audio = audio / 32768.0                                            # fad.py:148-149
         if audio.ndim > 1:                                                     # vggish.py:245-246 / pann.py:96-97
             audio = np.mean(audio, axis=1)
+        if sr != self.sample_rate and self.model_name == "clap":
+            # the reference pads to 480000 samples AT THE SOURCE RATE (fad.py:355-359) and int16-truncates
+            # (clap.py:70-72) before it resamples (clap.py:75-80); the front end's own quantisation is switched off for
+            # these clips (_embed_group).  Only the first 1001 frames survive (_pad_to_clap_time, fad.py:87-89), so the
+            # source is cut to what they can see plus a margin far wider than the resampling filter.
+            if audio.shape[0] < _CLAP_MAX_SAMPLES:
+                audio = np.pad(audio, (0, _CLAP_MAX_SAMPLES - audio.shape[0]))
+            keep = int((_CLAP_MAX_SAMPLES + 4096) * (float(sr) / float(self.sample_rate))) + 4096
+            audio = audio[:keep].astype(np.float32)
+            audio = (audio * np.float32(32767.0)).astype(np.int16).astype(np.float32) / np.float32(32767.0)
         if sr != self.sample_rate:                                             # vggish.py:249-250 / pann.py:100-101
             if device_resample:
                 n_out = int(audio.shape[0] * (float(self.sample_rate) / float(sr)))
@@ -292,6 +303,19 @@ class FrechetAudioDistance:
         out_host = torch.empty((n * rows, eng.dim), dtype=torch.float32).pin_memory()
         ring = self._ring()
         cur = torch.cuda.current_stream()
+        prequantised = resample_from is not None and self.model_name == "clap"      # see _prepare_clip
+        if prequantised:
+            eng.set_clap_quantize(False)
+        try:
+            self._embed_chunks(clips, n, chunk, rows, depth, st, ring, out_host, resample_from)
+        finally:
+            if prequantised:
+                eng.set_clap_quantize(True)
+        cur.synchronize()
+        return out_host.numpy()
+
+    def _embed_chunks(self, clips, n, chunk, rows, depth, st, ring, out_host, resample_from) -> None:
+        eng = self.engine
         slot = 0
         for c0 in range(0, n, chunk):
             nc = min(chunk, n - c0)
@@ -310,8 +334,6 @@ class FrechetAudioDistance:
             self._stage_ev[slot].record(ring.stream)
             self._stage_used[slot] = True
             slot = (slot + 1) % depth
-        cur.synchronize()
-        return out_host.numpy()
 
     def _chunk_clips(self, n_samples: int) -> int:
         """clips per host->device chunk: about 320 MB of fp32 PCM (512 ten-second 16 kHz clips were measured best on a

@@ -73,6 +73,10 @@ int fadb_set_precision(fadb_handle* h, int prec);
  * instead of ~1e-14.  Off by default: the reference computes np.cov in fp64 (fad.py:495), and the Frechet distance
  * of two SIMILAR sets amplifies a covariance error by tr(S) / FAD. */
 int fadb_set_tensor_syrk(fadb_handle* h, int on);
+/* CLAP only: whether the front end applies the int16 truncation of clap.py:70-72 to the samples it reads (default 1).
+ * The reference quantises BEFORE it resamples (clap.py:70-80), so a caller that resamples CLAP input itself quantises
+ * at the source rate and switches this off for that call (fad.py does, for get_embeddings(x, sr != 48000)). */
+int fadb_set_clap_quantize(fadb_handle* h, int on);
 /* max patches (VGGish) / clips (CNN14) per internal batch; sizes the activation workspace */
 int fadb_set_max_batch(fadb_handle* h, int max_items);
 

@@ -158,6 +158,33 @@ def test_clap_facade():
     assert np.max(np.abs(el - pipeline.OracleFAD("clap", sd).embed_clip(long))) / np.max(np.abs(ref)) < 1e-4
 
 
+def test_clap_foreign_sample_rate_follows_reference_order():
+    # get_embeddings(x, sr != 48000): the reference pads to 480000 samples at the SOURCE rate (fad.py:355-359),
+    # int16-truncates (clap.py:70-72), then resamples (clap.py:75-80) and keeps 1001 frames (fad.py:87-89)
+    from frechet_audio_distance_exported_b200 import FrechetAudioDistance
+    from frechet_audio_distance_exported_b200.resample import resample
+    from oracle import frontend
+    sd = networks.cnn14_random_state_dict(seed=2, clap_head=True)
+    fad = FrechetAudioDistance(model_name="clap", state_dict=sd, precision="bf16x3")
+    ora = pipeline.OracleFAD("clap", sd)
+    sr = 16000
+    clips = [(0.6 * synth.sine_clip(3.0, 440.0 + 60 * i, sr) + 0.05 * synth.background_clip(i, 3 * sr)).astype(np.float32)
+             for i in range(2)]
+    out = fad.get_embeddings(clips, sr)
+    assert out.shape == (2, 512)
+    for i, c in enumerate(clips):
+        padded = np.pad(c, (0, 480000 - c.shape[0]))
+        res = resample(frontend.clap_quantize(padded), sr, 48000).astype(np.float32)
+        lm = frontend.pann_logmel(res, 48000)[:1001]
+        ref = networks.clap_cnn14_forward(ora.sd, torch.from_numpy(lm)[None, None]).numpy()
+        assert np.max(np.abs(out[i] - ref[0])) / np.max(np.abs(ref)) < 1e-4
+    # the front end's own quantisation is back on afterwards: a native-rate clip still matches the oracle
+    a = synth.sine_clip(1.0, 440.0, 48000)
+    e = fad.get_embeddings([a], 48000)
+    r = ora.embed_clip(a)
+    assert np.max(np.abs(e - r)) / np.max(np.abs(r)) < 1e-4
+
+
 def test_encodec_is_out_of_scope():
     from frechet_audio_distance_exported_b200 import FrechetAudioDistance
     with pytest.raises(NotImplementedError):
