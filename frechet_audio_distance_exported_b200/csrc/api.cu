@@ -173,7 +173,8 @@ static int add_layer(fadb_handle* h, const float* w, int Cout, int Cin, int ksiz
     if (want_lo) FADB_CUDA_CHECK(cudaMalloc(&L.w_lo, n * sizeof(__nv_bfloat16)));
     FADB_CUDA_CHECK(cudaMalloc(&L.bias, (size_t)Cout * sizeof(float)));
     FADB_CHECK(pack_conv_weight(h, w, Cout, Cin, ksize, scale, L.w_hi, L.w_lo, L.f16 != 0, st));
-    if (h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && Cin % 128 == 0) {      // e4m3 low-order plane (gemm_tc.cu lo8)
+    // e4m3 low-order plane (gemm_tc.cu lo8; 64-channel 3x3 layers: c64)
+    if (h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && (Cin % 128 == 0 || (Cin == 64 && ksize == 3 && h->lo_fp8_c64))) {
         FADB_CUDA_CHECK(cudaMalloc(&L.w8, n));
         FADB_CHECK(pack_conv_weight_lo8(h, w, Cout, Cin, ksize, scale, L.w8, &L.lo_scale, st));
     }
@@ -290,8 +291,8 @@ static inline __nv_bfloat16* lo_plane(fadb_handle* h, int buf, size_t plane_elem
 constexpr size_t kVggishActElems = 98304;        // max activation elements per patch (48*32*64)
 
 // tensor-core part of VGGishCore: a1 = conv1 output [P,48,32,64] (hi/lo) -> emb [P,128]
-static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __nv_bfloat16* a1_lo, int64_t P,
-                            float* emb, cudaStream_t st) {
+static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __nv_bfloat16* a1_lo, const uint8_t* a1_8p,
+                            int64_t P, float* emb, cudaStream_t st) {
     // sized for THIS batch (the buffers only ever grow); the lo plane exists in the bf16x3 mode only
     const size_t plane = (size_t)P * kVggishActElems;                       // largest later activation: 24*16*256
     const size_t nplanes = h->precision == FADB_PREC_BF16X3 ? 2 : 1;
@@ -305,7 +306,7 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
         FADB_CHECK(h->ws_act8[1].reserve(plane));
         a8[0] = h->ws_act8[0].as<uint8_t>(); a8[1] = h->ws_act8[1].as<uint8_t>();
     }
-    const uint8_t* in8 = nullptr;                                           // conv1's 64-channel output has no e4m3 copy
+    const uint8_t* in8 = a1_8p;                                             // conv1's 64-channel output: W-padded e4m3 copy, or none
     const int B = (int)P;
     struct Step { int H, W, Cin, pool; };
     static const Step steps[5] = {{48, 32, 64, 1}, {24, 16, 128, 0}, {24, 16, 256, 1}, {12, 8, 256, 0}, {12, 8, 512, 1}};
@@ -319,6 +320,7 @@ static int vggish_tc_layers(fadb_handle* h, const __nv_bfloat16* a1_hi, const __
         io.taps = 9; io.relu = 1; io.pool = steps[i].pool;
         io.out_hi = a[cur]; io.out_lo = l[cur];
         io.in8 = in8; io.out8 = a8[cur];
+        io.in8_wpad = (i == 0);
         io.use_lo_weights = (h->x2_mask >> i) & 1u;
         FADB_CHECK(launch_gemm_layer(h, h->layers[i], io, st));
         in_hi = a[cur]; in_lo = l[cur]; in8 = a8[cur];
@@ -350,11 +352,23 @@ static inline __nv_bfloat16* a1_lo_plane(fadb_handle* h, int buf, int64_t P) {
     return h->ws_a1[buf].as<__nv_bfloat16>() + (size_t)P * kVggishActElems;
 }
 
+// W-padded e4m3 copy of conv1's output [P][48][34][64], when the first tensor-core layer's low-order pass wants it
+static int reserve_a1_8p(fadb_handle* h, int64_t P, uint8_t** out) {
+    *out = nullptr;
+    if (!(h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && h->lo_fp8_c64 && !h->layers.empty() && h->layers[0].w8)) return FADB_OK;
+    FADB_CHECK(h->ws_a1_8.reserve((size_t)P * 48 * 34 * 64));
+    *out = h->ws_a1_8.as<uint8_t>();
+    return FADB_OK;
+}
+
 static int vggish_forward(fadb_handle* h, const float* feats, int64_t P, float* emb, cudaStream_t st) {
     FADB_CHECK(reserve_a1(h, 0, P));
     __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
+    uint8_t* a1_8p = nullptr;
+    FADB_CHECK(reserve_a1_8p(h, P, &a1_8p));
     FADB_CHECK(launch_conv1_vggish(h, feats, P, a1, a1_lo_plane(h, 0, P), st));        // [P,48,32,64]
-    return vggish_tc_layers(h, a1, a1_lo_plane(h, 0, P), P, emb, st);
+    if (a1_8p) FADB_CHECK(quantize_e4m3_wpad(h, nullptr, a1, P * 48, 32, a1_8p, st));
+    return vggish_tc_layers(h, a1, a1_lo_plane(h, 0, P), a1_8p, P, emb, st);
 }
 
 // PCM -> embeddings for VGGish, chunked.  (A side stream running front end + conv1 of chunk i+1 under the tcgen05
@@ -372,9 +386,11 @@ static int vggish_embed_pcm(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t
             const int64_t Pc = nc * rows;
             FADB_CHECK(reserve_a1(h, 0, Pc));
             __nv_bfloat16* a1 = h->ws_a1[0].as<__nv_bfloat16>();
+            uint8_t* a1_8p = nullptr;
+            FADB_CHECK(reserve_a1_8p(h, Pc, &a1_8p));
             FADB_CHECK(launch_vggish_front_conv1(h, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride, a1,
-                                                 a1_lo_plane(h, 0, Pc), st));
-            FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0, Pc), Pc, emb + c0 * rows * d, st));
+                                                 a1_lo_plane(h, 0, Pc), a1_8p, st));
+            FADB_CHECK(vggish_tc_layers(h, a1, a1_lo_plane(h, 0, Pc), a1_8p, Pc, emb + c0 * rows * d, st));
         } else {
             FADB_CHECK(h->ws_feats.reserve((size_t)(n_clips < cpc ? n_clips : cpc) * rows * 96 * 64 * sizeof(float)));
             FADB_CHECK(launch_frontend(h, FADB_MODEL_VGGISH, pcm.offset(c0 * pcm_stride), nc, n_samples, pcm_stride,
@@ -515,6 +531,7 @@ int fadb_create(fadb_handle** out, int device) {
     if (const char* e = getenv("FADB_HALO")) h->halo = atoi(e);
     if (const char* e = getenv("FADB_TC_SYRK")) h->tc_syrk = atoi(e);
     if (const char* e = getenv("FADB_LO_FP8")) h->lo_fp8 = atoi(e);
+    if (const char* e = getenv("FADB_LO_FP8_C64")) h->lo_fp8_c64 = atoi(e);
     if (const char* e = getenv("FADB_X2_MASK")) h->x2_mask = (unsigned)strtoul(e, nullptr, 0);
     int rc = gemm_init(h);
     if (rc == FADB_OK) rc = frontend_init(h);
@@ -537,6 +554,7 @@ void fadb_destroy(fadb_handle* h) {
     h->ws_frechet.release(); h->ws_stats.release(); h->ws_pcm[0].release(); h->ws_pcm[1].release(); h->ws_emb.release();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->ws_a1[0].release();
+    h->ws_a1_8.release();
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
@@ -868,9 +886,11 @@ int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, i
     L.f16 = f16 ? 1 : 0;
     if (rc == FADB_OK) rc = pack_conv_weight(h, w_dev, Cout, Cin, ksize, nullptr, L.w_hi, L.w_lo, f16, st);
     uint8_t* x8 = nullptr;
-    if (rc == FADB_OK && h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && Cin % 128 == 0) {
-        if (cudaMalloc(&x8, n_in) != cudaSuccess || cudaMalloc(&L.w8, nw) != cudaSuccess) { set_error("cudaMalloc failed"); rc = FADB_E_NOMEM; }
-        if (rc == FADB_OK) rc = quantize_e4m3(h, x, (int64_t)n_in, x8, st);
+    const bool wpad = Cin == 64 && ksize == 3 && h->lo_fp8_c64;       // 64-channel layers: W-padded e4m3 input (GemmParams::c64)
+    if (rc == FADB_OK && h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && (Cin % 128 == 0 || wpad)) {
+        const size_t n8 = wpad ? (size_t)B * H * (W + 2) * Cin : n_in;
+        if (cudaMalloc(&x8, n8) != cudaSuccess || cudaMalloc(&L.w8, nw) != cudaSuccess) { set_error("cudaMalloc failed"); rc = FADB_E_NOMEM; }
+        if (rc == FADB_OK) rc = wpad ? quantize_e4m3_wpad(h, x, nullptr, (int64_t)B * H, W, x8, st) : quantize_e4m3(h, x, (int64_t)n_in, x8, st);
         if (rc == FADB_OK) rc = pack_conv_weight_lo8(h, w_dev, Cout, Cin, ksize, nullptr, L.w8, &L.lo_scale, st);
     }
     L.bias = const_cast<float*>(bias_dev);
@@ -879,6 +899,7 @@ int fadb_debug_conv_layer(fadb_handle* h, const float* x, int B, int H, int W, i
         io.in_hi = xh; io.in_lo = xl; io.B = B; io.H = H; io.W = W; io.Cin = Cin;
         io.taps = L.taps; io.relu = relu; io.pool = pool; io.out_f32 = out;
         io.in8 = x8;
+        io.in8_wpad = wpad ? 1 : 0;
         rc = launch_gemm_layer(h, L, io, st);
     }
     cudaError_t e = cudaStreamSynchronize(st);

@@ -144,6 +144,7 @@ struct fadb_handle {
 
     // activation workspace
     fadb::DevBuf ws_a1[1];      // conv1 output (input of the first tensor-core layer)
+    fadb::DevBuf ws_a1_8;       // its e4m3 copy, W-padded (fp16x2 with the e4m3 low-order pass: LayerIO::in8_wpad)
     fadb::DevBuf ws_feats;      // fp32 features of one batch
     fadb::DevBuf ws_act[2];     // ping-pong bf16 activations (hi plane followed by lo plane)
     fadb::DevBuf ws_act8[2];    // fp16x2: e4m3 copies of the same activations
@@ -151,6 +152,7 @@ struct fadb_handle {
     fadb::DevBuf ws_frechet;    // fp64 workspace of fadb_frechet
     fadb::DevBuf ws_stats;      // fp64 workspace of fadb_fad_from_pcm_host
     fadb::DevBuf ws_syrk;       // tensor-core syrk: transposed split-fp16 planes of one row chunk + its fp32 product
+    int lo_fp8_c64 = 1;         // ... and of the 64-channel 3x3 layers (two taps per 128-byte K block; FADB_LO_FP8_C64=0: fp16 pass)
     int clap_quantize = 1;      // CLAP front end applies clap.py:70-72's int16 truncation (fadb_set_clap_quantize)
     int tc_syrk = 0;            // 1: second moments of >= 8192 rows at d >= 512 on the tensor cores (fadb_set_tensor_syrk /
                                 // FADB_TC_SYRK): ~8x faster, covariance accurate to ~1e-6 instead of 1e-14 — OFF by default
@@ -184,7 +186,7 @@ int launch_frontend(fadb_handle* h, int model, PcmSrc pcm, int64_t n_clips, int6
 int frontend_init(fadb_handle* h);
 void frontend_release(fadb_handle* h);
 int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
-                              __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
+                              __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, uint8_t* out8p, cudaStream_t st);
 
 int64_t frontend_rows(int model, int64_t n_samples);
 
@@ -205,6 +207,8 @@ struct LayerIO {
     const __nv_bfloat16* in_lo = nullptr;     // may be null (bf16 mode)
     const uint8_t* in8 = nullptr;              // fp16x2: e4m3 copy of the input (for the e4m3 low-order weight pass)
     uint8_t* out8 = nullptr;                   // fp16x2: where to write the e4m3 copy of the output (Cout % 128 == 0)
+    int in8_wpad = 0;                          // in8 is [B][H][W+2][Cin] with a zero column left and right (64-channel layers:
+                                               // GemmParams::c64 reads it through overlapping two-pixel rows)
     int B = 0, H = 0, W = 0, Cin = 0;          // NHWC input; a linear layer is B=1,H=1,W=rows
     int taps = 9;                              // 9 = 3x3 pad 1, 1 = pointwise / linear
     int relu = 1;
@@ -234,6 +238,9 @@ int pack_conv_weight(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int
 int pack_conv_weight_lo8(fadb_handle* h, const float* w_oihw, int Cout, int Cin, int ksize, const float* scale,
                          uint8_t* w8, float* lo_scale, cudaStream_t st);
 int quantize_e4m3(fadb_handle* h, const float* x, int64_t n, uint8_t* out, cudaStream_t st);
+// [rows][W][64] fp32 or fp16 activations -> [rows][W+2][64] e4m3 with a zero column left and right (LayerIO::in8_wpad)
+int quantize_e4m3_wpad(fadb_handle* h, const float* x32, const __nv_bfloat16* x16, int64_t rows, int W, uint8_t* out,
+                       cudaStream_t st);
 int split_f32_to_bf16(fadb_handle* h, const float* x, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo, bool f16,
                       cudaStream_t st);
 int fold_bn(fadb_handle* h, const float* gamma, const float* beta, const float* mean, const float* var, int C,

@@ -462,7 +462,8 @@ struct FusedTcSmem {
 
 __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_tc_kernel(
     const FrontParams p, const float* __restrict__ conv_w, const float* __restrict__ conv_b, int patches_per_clip,
-    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int f16, int* err_flag, int dbg) {
+    int total_patches, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, uint8_t* __restrict__ out8p,
+    int f16, int* err_flag, int dbg) {
     constexpr int NF = 512, M = 256;
     using S = FrontSmem<NF>;
     using F = FusedTcSmem;
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                 const int prow = 4 * s + quarter;
                 const size_t obase = (((size_t)pi * 48 + prow) * 32 + lane) * 64 + half * 32;
                 const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + half * 32;
+                uint4 q8 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     uint32_t r0[16], r1[16], r2[16], r3[16];
@@ -604,6 +606,20 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) fadb_vggish_front_conv1_t
                     h1.x = pack_act2(g[8], g[9], f16); h1.y = pack_act2(g[10], g[11], f16);
                     h1.z = pack_act2(g[12], g[13], f16); h1.w = pack_act2(g[14], g[15], f16);
                     st_global_256(out_hi + obase + sub * 16, h0, h1);
+                    if (out8p) {    // e4m3 copy in the W-padded layout [P][48][34][64] (gemm_tc.cu GemmParams::c64)
+                        uint4 q;
+                        q.x = pack4_e4m3(g[0], g[1], g[2], g[3]);    q.y = pack4_e4m3(g[4], g[5], g[6], g[7]);
+                        q.z = pack4_e4m3(g[8], g[9], g[10], g[11]);  q.w = pack4_e4m3(g[12], g[13], g[14], g[15]);
+                        if (sub == 0) {
+                            q8 = q;                 // both 16-channel groups of this thread go out as one 32-byte store
+                        } else {
+                            uint8_t* o8 = out8p + (((size_t)pi * 48 + prow) * 34 + lane + 1) * 64 + half * 32;
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                            st_global_256(o8, q8, q);
+                            if (lane == 0) st_global_256(o8 - 64, z, z);        // zero column 0
+                            if (lane == 31) st_global_256(o8 + 64, z, z);       // zero column 33
+                        }
+                    }
                     if (out_lo) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) g[j] -= bf16_round(g[j]);
@@ -799,7 +815,7 @@ struct FrontProfile {
 
 // PCM -> conv1 output [n_clips * patches, 48, 32, 64] bf16 (hi / optional lo) in one kernel (VGGish only)
 int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64_t n_samples, int64_t pcm_stride,
-                              __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+                              __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, uint8_t* out8p, cudaStream_t st) {
     FADB_CHECK(build_tables(h, FADB_MODEL_VGGISH));
     const FrontTables& t = h->front_tables[FADB_MODEL_VGGISH];
     const int64_t patches = frontend_rows(FADB_MODEL_VGGISH, n_samples);
@@ -824,7 +840,7 @@ int launch_vggish_front_conv1(fadb_handle* h, PcmSrc pcm, int64_t n_clips, int64
     const int64_t total = patches * n_clips;
     const int64_t slots = 2LL * h->sm_count;
     fadb_vggish_front_conv1_tc_kernel<<<(unsigned)(total < slots ? total : slots), kFrontWarps * 32, FusedTcSmem::kTotal, st>>>(
-        p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo, (int)prec_is_f16(h->precision), h->err_flag, front_dbg);
+        p, h->conv1_w, h->conv1_b, (int)patches, (int)total, out_hi, lo, out8p, (int)prec_is_f16(h->precision), h->err_flag, front_dbg);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;

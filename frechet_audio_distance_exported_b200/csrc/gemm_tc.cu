@@ -66,6 +66,10 @@ struct GemmParams {
                           // its segment sums are scaled by lo_scale = 2^-s when the epilogue adds them in
     int kb0;              // K blocks of pass 0 (taps * cin_blocks)
     int cin_blocks1;      // channel blocks of pass 1: Cin / 128 when lo8
+    int c64;              // lo8 on a 64-CHANNEL 3x3 layer (halo mode only): tmH8 views the W-padded e4m3 tensor
+                          // [B][H][W+2][64] with OVERLAPPING 128-byte rows [pixel x | pixel x+1], so one 128-byte K block is
+                          // the taps (ky,0),(ky,1) of a filter row and a second block, half used, is the tap (ky,2):
+                          // 6 weight K blocks and 18 e4m3 MMAs per tile instead of 9 blocks and 36 fp16 MMAs
     int nseg0;            // accumulation segments of pass 0 (lo8: segments never straddle the pass boundary)
     int seg_len1;         // segment length of pass 1
     float lo_scale;
@@ -271,8 +275,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 if (elect_one()) {
                     expect(bar_bres, (uint32_t)res_bytes);
                     for (int kbg = 0; kbg < p.nkb; ++kbg) {                  // resident layout: [plane][tap][channel block]
-                        if (LO8 && kbg >= p.kb0)                              // e4m3 lo plane: 128 channels per block
-                            load_wgt(bar_bres, base + kbg * kBTile, (kbg - p.kb0) * 128, 0, 2);
+                        if (LO8 && kbg >= p.kb0) {                            // e4m3 lo plane: 128 channels per block
+                            const int j = kbg - p.kb0;                        // c64: taps (ky,0..1) at 3 ky * 64, tap (ky,2) at (3 ky + 2) * 64
+                            load_wgt(bar_bres, base + kbg * kBTile, p.c64 ? (3 * (j >> 1) + 2 * (j & 1)) * 64 : j * 128, 0, 2);
+                        }
                         else {
                             const int plane = kbg / kb_per_pass;
                             load_wgt(bar_bres, base + kbg * kBTile, (kbg - plane * kb_per_pass) * kBlockK, 0, plane);
@@ -295,8 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u, p.err_flag);
                     if (elect_one()) {
                         expect(bar_full + 8 * stage, (uint32_t)kHaloBoxBytes);
+                        // (c64: the e4m3 tensor carries a zero column left and right, so halo column -1 is row 0 of the view)
                         load_act(f8 ? &p.tmH8 : &p.tmH, bar_full + 8 * stage, stage_base + stage * kHaloBytes,
-                                 f8 ? (t - p.cin_blocks) * 128 : t * kBlockK, wt * p.BW - 1, ht * p.BH - 1, bt);
+                                 f8 ? (t - p.cin_blocks) * 128 : t * kBlockK, wt * p.BW - 1 + ((f8 && p.c64) ? 1 : 0),
+                                 ht * p.BH - 1, bt);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -386,6 +394,18 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                     const bool f8 = LO8 && t >= p.cin_blocks;                        // lo8: pass-1 tiles come after all pass-0 tiles
                     const int cb = f8 ? t - p.cin_blocks : t;
                     const int planes = LO8 ? 1 : p.npass;
+                    if (LO8 && f8 && p.c64) {
+                        for (int j = 0; j < 6; ++j) {                         // K blocks (ky, kx 0..1) and (ky, kx 2) of the three filter rows
+                            mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
+                            if (elect_one()) {
+                                expect(bar_bfull + 8 * bs, (uint32_t)kBTile);
+                                load_wgt(bar_bfull + 8 * bs, bring_base + bs * kBTile, (3 * (j >> 1) + 2 * (j & 1)) * 64, n0, 2);
+                            }
+                            __syncwarp();
+                            if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+                        }
+                        continue;
+                    }
                     for (int tap = 0; tap < 9; ++tap) {
                         for (int plane = 0; plane < planes; ++plane) {        // fp16 lo pass: the hi and the lo weight tile of this tap
                             mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u, p.err_flag);
@@ -442,6 +462,42 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                 const uint64_t da0 = make_halo_desc(stage_base + stage * kHaloBytes);
                 // The MMA issue sequence of a tile is kept free of data-dependent branches (the e4m3 / fp16 choice is made
                 // once per tile, outside the unrolled loops): a branch between two tcgen05.mma issues costs more than the MMA.
+                // c64 e4m3 tile: per filter row one full K block (taps kx = 0, 1: 4 MMAs of 32 bytes) at view column 0 and
+                // one half-used block (tap kx = 2: 2 MMAs) at view column 2
+                auto issue_tile_c64 = [&]() {
+                    if (p.resb) {
+                        if (elect_one()) {
+                            const uint64_t db0 = make_sw128_desc(base + p.kb0 * kBTile);
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) {
+                                const uint64_t da = da0 + (uint64_t)(((j >> 1) * kHaloW + 2 * (j & 1)) * 8);
+                                const uint64_t db = db0 + (uint64_t)(j * ((uint32_t)kBTile >> 4));
+#pragma unroll
+                                for (int k = 0; k < ((j & 1) ? 2 : 4); ++k)
+                                    mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | j | k) != 0 ? 1u : 0u);
+                            }
+                            commit(bar_empty + 8 * stage);
+                        }
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            const uint64_t da = da0 + (uint64_t)(((j >> 1) * kHaloW + 2 * (j & 1)) * 8);
+                            mbar_wait(bar_bfull + 8 * bs, bphase, p.err_flag);
+                            tc_fence_after();
+                            const uint64_t db = make_sw128_desc(bring_base + bs * kBTile);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < ((j & 1) ? 2 : 4); ++k)
+                                    mma8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first | j | k) != 0 ? 1u : 0u);
+                                commit(bar_bempty + 8 * bs);
+                                if (j == 5) commit(bar_empty + 8 * stage);
+                            }
+                            __syncwarp();
+                            if (++bs == p.b_stages) { bs = 0; bphase ^= 1u; }
+                        }
+                    }
+                };
                 auto issue_tile = [&](auto f8tag) {
                     constexpr bool F8 = decltype(f8tag)::value;
                     if (p.resb) {
@@ -489,8 +545,12 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                         }
                     }
                 };
-                if (f8) issue_tile(std::true_type{});
-                else issue_tile(std::false_type{});
+                bool done = false;
+                if constexpr (LO8) if (f8 && p.c64) { issue_tile_c64(); done = true; }
+                if (!done) {
+                    if (f8) issue_tile(std::true_type{});
+                    else issue_tile(std::false_type{});
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 // segment complete (also at the pass boundary and at the end of the tile) -> epilogue adds it in
                 if (--seg_left == 0 || t == a_tiles - 1 || (LO8 && t == p.cin_blocks - 1)) {
@@ -871,6 +931,24 @@ static int encode_act_map(CUtensorMap* tm, const void* ptr, int C, int W, int H,
     return FADB_OK;
 }
 
+// GemmParams::c64: the W-padded e4m3 tensor [B][H][W+2][64] as rows of 128 bytes that OVERLAP by 64 (row r = padded
+// pixels r, r+1); W+1 rows per image row.  (tools/tma_overlap_probe.cu: a W stride below the innermost extent encodes
+// and loads as expected.)
+static int encode_act_map_c64(CUtensorMap* tm, const void* ptr, int W, int H, int B) {
+    cuuint64_t dims[4] = {128, (cuuint64_t)(W + 1), (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {64, (cuuint64_t)(W + 2) * 64, (cuuint64_t)H * (W + 2) * 64};
+    cuuint32_t box[4] = {128, (cuuint32_t)kHaloW, 18, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(e4m3 activations, overlapping rows, W=%d H=%d B=%d) failed: %d", W, H, B, (int)r);
+        return FADB_E_CUDA;
+    }
+    return FADB_OK;
+}
+
 static int encode_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int BN, int kind, long long rs = 0) {
     if (rs <= 0) rs = K;
     const cuuint64_t es = kind == 2 ? 1 : 2;
@@ -953,7 +1031,10 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     memset(&p, 0, sizeof(p));
     // fp16x2: the low-order weight pass in e4m3 (twice the MMA rate, half the operand bytes) where the layer has whole
     // 128-channel blocks and both e4m3 operands exist
-    const bool lo8 = npass == 2 && !io.syrk && h->lo_fp8 && io.in8 && L.w8 && io.Cin % 128 == 0;
+    // 64-channel 3x3 layers in halo mode: the same with two taps per 128-byte K block (GemmParams::c64); their e4m3 input
+    // is the W-padded layout (io.in8_wpad)
+    const bool c64 = npass == 2 && !io.syrk && h->lo_fp8 && io.in8 && io.in8_wpad && L.w8 && io.Cin == 64 && halo;
+    const bool lo8 = c64 || (npass == 2 && !io.syrk && h->lo_fp8 && io.in8 && !io.in8_wpad && L.w8 && io.Cin % 128 == 0);
     FADB_CHECK(encode_act_map(&p.tmA[0], io.in_hi, io.Cin, io.W, io.H, io.B, BW, BH, BB, f16, io.row_stride));
     if (halo) FADB_CHECK(encode_act_map(&p.tmH, io.in_hi, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1, f16));
     else p.tmH = p.tmA[0];
@@ -966,12 +1047,16 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.tmA[2] = p.tmA[0];
     p.tmB[2] = p.tmB[0];
     p.tmH8 = p.tmH;
-    if (lo8) {
+    if (c64) {
+        FADB_CHECK(encode_act_map_c64(&p.tmH8, io.in8, io.W, io.H, io.B));
+        FADB_CHECK(encode_weight_map(&p.tmB[2], L.w8, L.K, L.N, BN, 2));
+    } else if (lo8) {
         FADB_CHECK(encode_act_map(&p.tmA[2], io.in8, io.Cin, io.W, io.H, io.B, BW, BH, BB, 2));
         if (halo) FADB_CHECK(encode_act_map(&p.tmH8, io.in8, io.Cin, io.W, io.H, io.B, kHaloW, 18, 1, 2));
         FADB_CHECK(encode_weight_map(&p.tmB[2], L.w8, L.K, L.N, BN, 2));
     }
     p.lo8 = lo8 ? 1 : 0;
+    p.c64 = c64 ? 1 : 0;
     p.lo_scale = lo8 ? L.lo_scale : 1.f;
     p.W = io.W; p.H = io.H; p.B = io.B;
     p.BW = BW; p.BH = BH; p.BB = BB;
@@ -1154,8 +1239,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     // accumulation segments (GemmParams::nseg): chains of at most kSegmentBlocks K blocks (64 MMAs); in halo mode a
     // segment is a whole number of channel blocks (9 * npass K blocks each)
     p.kb0 = io.taps * p.cin_blocks;
-    p.cin_blocks1 = lo8 ? io.Cin / 128 : p.cin_blocks;
-    p.nkb = lo8 ? p.kb0 + io.taps * p.cin_blocks1 : npass * io.taps * p.cin_blocks;
+    p.cin_blocks1 = c64 ? 1 : (lo8 ? io.Cin / 128 : p.cin_blocks);
+    p.nkb = c64 ? p.kb0 + 6 : (lo8 ? p.kb0 + io.taps * p.cin_blocks1 : npass * io.taps * p.cin_blocks);
     auto split = [](int n, int kseg, int& nseg, int& len) {          // n K blocks into chains of <= kseg, evenly
         nseg = (n + kseg - 1) / kseg;
         len = (n + nseg - 1) / nseg;

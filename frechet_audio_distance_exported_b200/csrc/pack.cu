@@ -92,6 +92,35 @@ __global__ void quantize_e4m3_kernel(const float* __restrict__ x, size_t n, uint
         out[i] = to_e4m3(x[i]);
 }
 
+// one thread per 16 output bytes; pixel column 0 and W+1 of every row are zero
+__global__ void quantize_e4m3_wpad_kernel(const float* __restrict__ x32, const __half* __restrict__ x16, size_t rows, int W,
+                                          uint8_t* __restrict__ out) {
+    const size_t total = rows * (size_t)(W + 2) * 4;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int q = int(i & 3);
+        const size_t px = i >> 2;
+        const int xp = int(px % (size_t)(W + 2));
+        const size_t row = px / (size_t)(W + 2);
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (xp > 0 && xp <= W) {
+            const size_t src = (row * W + (xp - 1)) * 64 + q * 16;
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float f = x32 ? x32[src + 4 * k + e] : __half2float(x16[src + 4 * k + e]);
+                    v |= (uint32_t)to_e4m3(f) << (8 * e);
+                }
+                w[k] = v;
+            }
+            o = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+}
+
 static inline int grid_for(size_t n) {
     size_t g = (n + 255) / 256;
     return (int)(g > 4096 ? 4096 : (g ? g : 1));
@@ -133,6 +162,16 @@ int pack_conv_weight_lo8(fadb_handle* h, const float* w_oihw, int Cout, int Cin,
 int quantize_e4m3(fadb_handle* h, const float* x, int64_t n, uint8_t* out, cudaStream_t st) {
     if (n <= 0) return FADB_OK;
     quantize_e4m3_kernel<<<grid_for((size_t)n), 256, 0, st>>>(x, (size_t)n, out);
+    h->launches++;
+    FADB_CUDA_CHECK(cudaGetLastError());
+    return FADB_OK;
+}
+
+int quantize_e4m3_wpad(fadb_handle* h, const float* x32, const __nv_bfloat16* x16, int64_t rows, int W, uint8_t* out,
+                       cudaStream_t st) {
+    if (rows <= 0) return FADB_OK;
+    const size_t total = (size_t)rows * (size_t)(W + 2) * 4;
+    quantize_e4m3_wpad_kernel<<<grid_for(total), 256, 0, st>>>(x32, reinterpret_cast<const __half*>(x16), (size_t)rows, W, out);
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;
