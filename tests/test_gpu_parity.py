@@ -109,8 +109,47 @@ def test_tcgen05_layer_matches_conv2d(eng_bare, prec, case):
     ref = F.max_pool2d(ref, 2) if pool == 1 else (F.avg_pool2d(ref, 2) if pool == 2 else ref)
     ref = ref.permute(0, 2, 3, 1).numpy()
     assert out.shape == ref.shape
-    # fp16x2 multiplies the low-order weight plane in e4m3 where Cin % 128 == 0 (a 2^-12 correction known to ~6 %)
+    # fp16x2 multiplies the low-order weight plane in e4m3 where Cin % 128 == 0, and on 64-channel halo-mode layers
+    # (a 2^-12 correction known to ~6 %)
     assert relerr(out, ref) < (1e-4 if prec == "bf16x3" else (5e-5 if prec == "fp16x2" else 2e-5))
+
+
+def test_e4m3_low_order_pass_of_64_channel_layers(vgg_sd, monkeypatch):
+    """fp16x2 on a 64-channel 3x3 layer in halo mode (VGGish conv2): the low-order pass runs in e4m3 with two taps per
+    128-byte K block through the overlapping-row view of the W-padded e4m3 input (gemm_tc.cu GemmParams::c64).  It must
+    agree with the fp16 low-order pass (FADB_LO_FP8_C64=0) to the size of the e4m3 rounding of a 2^-12 correction —
+    with resident weights, with the weight ring, at a ragged H and a map one tile wide — and through the whole network
+    from PCM (fused front end writes the padded e4m3 plane) and from features (separate pad + quantise kernel)."""
+    from frechet_audio_distance_exported_b200 import Engine
+    on = Engine("vggish", vgg_sd, precision="fp16x2")
+    monkeypatch.setenv("FADB_LO_FP8_C64", "0")
+    off = Engine("vggish", vgg_sd, precision="fp16x2")
+    for case in [(2, 48, 32, 64, 128, 3, 1, 1), (3, 60, 16, 64, 128, 3, 1, 2), (1, 129, 8, 64, 128, 3, 1, 2),
+                 (2, 32, 24, 64, 256, 3, 1, 0), (1, 16, 8, 64, 64, 3, 0, 0)]:
+        B, H, W, Cin, Cout, k, relu, pool = case
+        g = torch.Generator().manual_seed(hash(case) % 1000)
+        x = torch.randn((B, H, W, Cin), generator=g)
+        w = torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5
+        b = torch.randn(Cout, generator=g) * 0.1
+        a = on.debug_conv_layer(x.cuda(), w.cuda(), b.cuda(), k, bool(relu), pool).cpu().numpy()
+        c = off.debug_conv_layer(x.cuda(), w.cuda(), b.cuda(), k, bool(relu), pool).cpu().numpy()
+        ref = F.conv2d(x.half().float().permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1)
+        ref = F.relu(ref) if relu else ref
+        ref = F.max_pool2d(ref, 2) if pool == 1 else (F.avg_pool2d(ref, 2) if pool == 2 else ref)
+        ref = ref.permute(0, 2, 3, 1).numpy()
+        assert not np.array_equal(a, c), case                  # the e4m3 pass is really the one that ran
+        assert relerr(a, ref) < 5e-5 and relerr(c, ref) < 5e-6, (case, relerr(a, ref), relerr(c, ref))
+    # Through the network the two variants are two equally good fp16 computations: a 1e-5 change after conv2 flips fp16
+    # roundings downstream, so they differ from EACH OTHER by about what each differs from the oracle (7e-4 of the
+    # largest embedding value, the fp16 activation rounding), not by the size of the conv2 change.
+    clips = synth.clip_set(0, 0, 3, 2 * 16000 + 400, 16000)
+    pcm = torch.from_numpy(clips).cuda()
+    ref = pipeline.OracleFAD("vggish", vgg_sd).get_embeddings(list(clips))
+    e_on, e_off = on.embed_pcm(pcm).cpu().numpy(), off.embed_pcm(pcm).cpu().numpy()
+    tol = PRECISIONS["fp16x2"][0]
+    assert not np.array_equal(e_on, e_off)
+    assert relerr(e_on, ref) < tol and relerr(e_off, ref) < tol and relerr(e_on, e_off) < tol
+    assert relerr(on.embed_features(on.frontend(pcm)).cpu().numpy(), ref) < tol
 
 
 PAIR_MODES = {
