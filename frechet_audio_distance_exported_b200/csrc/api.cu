@@ -412,13 +412,16 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
     __nv_bfloat16* l[2] = {lo_plane(h, 0, plane), lo_plane(h, 1, plane)};
     uint8_t* a8[2] = {nullptr, nullptr};                                    // e4m3 copies (fp16x2 with the e4m3 lo pass)
     if (h->precision == FADB_PREC_FP16X2 && h->lo_fp8) {
-        // the 64-channel maps of block 1 need none: the largest map with a copy is block 2's [B, T/2, 32, 128]
-        FADB_CHECK(h->ws_act8[0].reserve(plane / 2));
+        // the largest map with an unpadded copy is block 2's [B, T/2, 32, 128]; the 64-channel maps of block 1 get
+        // W-padded copies (c64): conv1's [B, T, 66, 64] in a8[0], conv1_2's pooled [B, T/2, 34, 64] in a8[1]
+        const bool c64 = h->lo_fp8_c64 && !h->layers.empty() && h->layers[0].w8;
+        FADB_CHECK(h->ws_act8[0].reserve(c64 ? plane / 64 * 66 : plane / 2));
         FADB_CHECK(h->ws_act8[1].reserve(plane / 2));
         a8[0] = h->ws_act8[0].as<uint8_t>(); a8[1] = h->ws_act8[1].as<uint8_t>();
     }
-    bool have8 = false;                                                     // does a8[cur] hold the current activations?
-    FADB_CHECK(launch_conv1_cnn14(h, feats, B, T, a[0], l[0], st));                     // [B,T,64,64]
+    const bool c64 = a8[0] && h->lo_fp8_c64 && !h->layers.empty() && h->layers[0].w8;
+    bool have8 = c64;                                                       // does a8[cur] hold the current activations?
+    FADB_CHECK(launch_conv1_cnn14(h, feats, B, T, a[0], l[0], c64 ? a8[0] : nullptr, st));   // [B,T,64,64]
     int cur = 0, H = T, W = 64, C = 64, li = 0;
     for (int blk = 1; blk <= 6; ++blk) {
         for (int cv = 1; cv <= 2; ++cv) {
@@ -430,7 +433,9 @@ static int cnn14_forward(fadb_handle* h, const float* feats, int64_t B64, int T,
             io.pool = (cv == 2 && blk < 6) ? 2 : 0;                                     // avg_pool2d, pann.py:192,255-260
             io.out_hi = a[cur ^ 1]; io.out_lo = l[cur ^ 1];
             io.in8 = have8 ? a8[cur] : nullptr;
-            io.out8 = (h->layers[li].N % 128 == 0) ? a8[cur ^ 1] : nullptr;
+            io.in8_wpad = (have8 && C == 64) ? 1 : 0;                                   // block 1's maps and conv2_1's input
+            io.out8_wpad = (c64 && h->layers[li].N == 64) ? 1 : 0;                      // conv1_2 -> conv2_1
+            io.out8 = (h->layers[li].N % 128 == 0 || io.out8_wpad) ? a8[cur ^ 1] : nullptr;
             io.use_lo_weights = (h->x2_mask >> li) & 1u;
             FADB_CHECK(launch_gemm_layer(h, h->layers[li], io, st));
             have8 = io.out8 != nullptr;

@@ -199,7 +199,7 @@ int launch_resample(fadb_handle* h, const float* in, int64_t n_clips, int64_t n_
 int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, __nv_bfloat16* out_hi,
                         __nv_bfloat16* out_lo, cudaStream_t st);
 int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int T, __nv_bfloat16* out_hi,
-                       __nv_bfloat16* out_lo, cudaStream_t st);
+                       __nv_bfloat16* out_lo, uint8_t* out8p, cudaStream_t st);
 
 // gemm_tc.cu — tcgen05 implicit-GEMM layer
 struct LayerIO {
@@ -207,6 +207,7 @@ struct LayerIO {
     const __nv_bfloat16* in_lo = nullptr;     // may be null (bf16 mode)
     const uint8_t* in8 = nullptr;              // fp16x2: e4m3 copy of the input (for the e4m3 low-order weight pass)
     uint8_t* out8 = nullptr;                   // fp16x2: where to write the e4m3 copy of the output (Cout % 128 == 0)
+    int out8_wpad = 0;                         // write out8 in that W-padded layout (the consumer is a 64-channel layer)
     int in8_wpad = 0;                          // in8 is [B][H][W+2][Cin] with a zero column left and right (64-channel layers:
                                                // GemmParams::c64 reads it through overlapping two-pixel rows)
     int B = 0, H = 0, W = 0, Cin = 0;          // NHWC input; a linear layer is B=1,H=1,W=rows

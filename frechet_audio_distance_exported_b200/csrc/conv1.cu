@@ -9,6 +9,7 @@
 //            feats [B,T,64] -> [B,T,64,64]
 #include "common.cuh"
 #include "conv1_dev.cuh"
+#include "tc_ptx.cuh"
 
 namespace fadb {
 
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __rest
                                                              const float* __restrict__ bn0_shift,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ out_hi,
-                                                             __nv_bfloat16* __restrict__ out_lo, int f16) {
+                                                             __nv_bfloat16* __restrict__ out_lo,
+                                                             uint8_t* __restrict__ out8p, int f16) {
     constexpr int W = 64;
     __shared__ float s_in[kC14Rows + 2][W + 2];
     __shared__ __align__(16) float s_w[9][64];
@@ -133,6 +135,13 @@ __global__ void __launch_bounds__(256, 2) conv1_cnn14_kernel(const float* __rest
                     v[2 * j + 1] = fmaxf(a1 + bb.y, 0.f);
                 }
                 store16(v, out_hi, out_lo, ((size_t(clip) * T + y) * W + x) * 64 + g * 16, f16);
+                if (out8p) {    // e4m3 copy, W-padded [B][T][66][64] (gemm_tc.cu GemmParams::c64)
+                    uint8_t* o8 = out8p + ((size_t(clip) * T + y) * (W + 2) + x + 1) * 64 + g * 16;
+                    *reinterpret_cast<uint4*>(o8) = make_uint4(pack4_e4m3(v[0], v[1], v[2], v[3]), pack4_e4m3(v[4], v[5], v[6], v[7]),
+                                                               pack4_e4m3(v[8], v[9], v[10], v[11]), pack4_e4m3(v[12], v[13], v[14], v[15]));
+                    if (x == 0) *reinterpret_cast<uint4*>(o8 - 64) = make_uint4(0u, 0u, 0u, 0u);
+                    if (x == W - 1) *reinterpret_cast<uint4*>(o8 + 64) = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
         }
     }
@@ -151,14 +160,15 @@ int launch_conv1_vggish(fadb_handle* h, const float* feats, int64_t n_patches, _
 }
 
 int launch_conv1_cnn14(fadb_handle* h, const float* feats, int64_t n_clips, int T, __nv_bfloat16* out_hi,
-                       __nv_bfloat16* out_lo, cudaStream_t st) {
+                       __nv_bfloat16* out_lo, uint8_t* out8p, cudaStream_t st) {
     if (n_clips <= 0) return FADB_OK;
     FADB_REQUIRE(n_clips <= 65535, "conv1: at most 65535 clips per batch");
     // (a tcgen05 version of this kernel, like the fused VGGish one, measured the same 0.22 ms per 64 clips: the
     // kernel is bound by writing its 8.45 MB of bf16 activations per clip to HBM, so the CUDA-core version stays)
     dim3 grid((unsigned)((T + kC14Rows - 1) / kC14Rows), (unsigned)n_clips);
     conv1_cnn14_kernel<<<grid, 256, 0, st>>>(feats, T, h->bn0_scale, h->bn0_shift, h->conv1_w, h->conv1_b, out_hi,
-                                            h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr, (int)prec_is_f16(h->precision));
+                                            h->precision == FADB_PREC_BF16X3 ? out_lo : nullptr, out8p,
+                                            (int)prec_is_f16(h->precision));
     h->launches++;
     FADB_CUDA_CHECK(cudaGetLastError());
     return FADB_OK;

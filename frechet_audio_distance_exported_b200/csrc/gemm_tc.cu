@@ -74,6 +74,7 @@ struct GemmParams {
     int seg_len1;         // segment length of pass 1
     float lo_scale;
     uint8_t* out8;        // e4m3 copy of the output (the next layer's pass-1 activations), or nullptr
+    int out8_wpad;        // 1: out8 is [B][Ho][Wo+2][N] with a zero column left and right (input layout of a c64 layer)
     int nseg, seg_len;    // accumulation segments per tile and their length (K blocks; halo mode: channel blocks).
                           // Each segment is its own accumulation chain in tensor memory (the two TMEM accumulators
                           // alternate per SEGMENT); the epilogue warps add the segment sums in fp32 registers with
@@ -688,14 +689,17 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
             const int bt = m / p.tiles_h;
             const int x = wt * p.BW + ww, y = ht * p.BH + hh, b = bt * p.BB + bb;
             bool valid;
-            size_t obase;
-            if (p.pool) {
-                const int px = x >> 1, py = y >> 1;
-                valid = px < p.Wo && py < p.Ho && b < p.B;          // all 4 lanes of a window store (8 channels each)
-                obase = ((size_t(b) * p.Ho + py) * p.Wo + px) * p.N + n0;
-            } else {
-                valid = x < p.W && y < p.H && b < p.B;
-                obase = ((size_t(b) * p.Ho + y) * p.Wo + x) * p.N + n0;
+            size_t obase, o8base;                    // o8base: the same pixel in the (possibly W-padded) e4m3 copy
+            int edge = 0;                            // W-padded e4m3 copy: -1 / +1 = this pixel also zeroes the column left / right of it
+            {
+                const int ox = p.pool ? (x >> 1) : x, oy = p.pool ? (y >> 1) : y;
+                valid = ox < p.Wo && oy < p.Ho && b < p.B;          // pooling: all 4 lanes of a window store (8 channels each)
+                obase = ((size_t(b) * p.Ho + oy) * p.Wo + ox) * p.N + n0;
+                o8base = obase;
+                if (F16 && p.out8_wpad) {
+                    o8base = ((size_t(b) * p.Ho + oy) * (p.Wo + 2) + ox + 1) * p.N + n0;
+                    edge = ox == 0 ? -1 : (ox == p.Wo - 1 ? 1 : 0);
+                }
             }
 
             // ---- add the tile's accumulation segments in fp32 registers (round-to-nearest): run[ci][j] = this row's
@@ -801,9 +805,13 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             hi.x = pack_act2<F16>(g8[0], g8[1]); hi.y = pack_act2<F16>(g8[2], g8[3]);
                             hi.z = pack_act2<F16>(g8[4], g8[5]); hi.w = pack_act2<F16>(g8[6], g8[7]);
                             *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
-                            if (F16 && p.out8)
-                                *reinterpret_cast<uint2*>(p.out8 + o) = make_uint2(pack4_e4m3(g8[0], g8[1], g8[2], g8[3]),
-                                                                                   pack4_e4m3(g8[4], g8[5], g8[6], g8[7]));
+                            if (F16 && p.out8) {
+                                uint8_t* o8 = p.out8 + o8base + (o - obase);
+                                *reinterpret_cast<uint2*>(o8) = make_uint2(pack4_e4m3(g8[0], g8[1], g8[2], g8[3]),
+                                                                           pack4_e4m3(g8[4], g8[5], g8[6], g8[7]));
+                                if (edge != 0) *reinterpret_cast<uint2*>(o8 + edge * p.N) = make_uint2(0u, 0u);
+                                if (edge < 0 && p.Wo == 1) *reinterpret_cast<uint2*>(o8 + p.N) = make_uint2(0u, 0u);
+                            }
                             if (!F16 && p.out_lo) {
                                 uint4 lo;
                                 lo.x = pack_bf16x2(g8[0] - bf16_round(g8[0]), g8[1] - bf16_round(g8[1]));
@@ -841,7 +849,13 @@ __global__ void __launch_bounds__(kThreads, 1) fadb_gemm_tc_kernel(const __grid_
                             q0.z = pack4_e4m3(v[8], v[9], v[10], v[11]);   q0.w = pack4_e4m3(v[12], v[13], v[14], v[15]);
                             q1.x = pack4_e4m3(v[16], v[17], v[18], v[19]); q1.y = pack4_e4m3(v[20], v[21], v[22], v[23]);
                             q1.z = pack4_e4m3(v[24], v[25], v[26], v[27]); q1.w = pack4_e4m3(v[28], v[29], v[30], v[31]);
-                            st_global_256(p.out8 + o, q0, q1);
+                            uint8_t* o8 = p.out8 + o8base + c * 32;
+                            st_global_256(o8, q0, q1);
+                            if (edge != 0) {
+                                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                                st_global_256(o8 + edge * p.N, z, z);
+                                if (edge < 0 && p.Wo == 1) st_global_256(o8 + p.N, z, z);
+                            }
                         }
                         if (!F16 && p.out_lo) {
                             uint4 lo[4];
@@ -1081,7 +1095,8 @@ int launch_gemm_layer(fadb_handle* h, const PackedLayer& L, const LayerIO& io, c
     p.upper_only = io.syrk;
     p.out_f32 = io.out_f32;
     p.out_f64 = io.out_f64;
-    p.out8 = (h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && !io.out_f32 && L.N % 128 == 0) ? io.out8 : nullptr;
+    p.out8 = (h->precision == FADB_PREC_FP16X2 && h->lo_fp8 && !io.out_f32 && (L.N % 128 == 0 || io.out8_wpad)) ? io.out8 : nullptr;
+    p.out8_wpad = (p.out8 && io.out8_wpad) ? 1 : 0;
     p.err_flag = h->err_flag;
     FADB_REQUIRE(p.out_f32 || p.out_hi || p.out_f64, "layer has no output buffer");
 

@@ -249,6 +249,22 @@ class FrechetAudioDistance:
         self._check_length(audio.shape[0])
         return audio
 
+    def _canonical_length(self, a: np.ndarray) -> np.ndarray:
+        """Clips of different lengths that the model cannot tell apart get ONE length, so that a directory of ragged
+        clips becomes a handful of device batches instead of one per distinct length.  VGGish keeps whole 0.96 s patches
+        only (vggish.py:268-277): samples past the last complete patch are never read, so clips are cut to
+        (96 P - 1) * 160 + 400 samples.  CLAP input is zero-padded to 480 000 samples anyway (fad.py:355-359).  Both are
+        exact; CNN14/PANN pools over every frame of the clip and keeps its own length."""
+        n = a.shape[0]
+        if self.model_name == "vggish":
+            patches = self.engine.frontend_rows(n)
+            need = (96 * patches - 1) * 160 + 400
+            if 0 < patches and need < n:
+                return a[:need]
+        elif self.model_name == "clap" and n < _CLAP_MAX_SAMPLES:
+            return np.pad(a, (0, _CLAP_MAX_SAMPLES - n))
+        return a
+
     def get_embeddings(self, x: List[np.ndarray], sr: int) -> np.ndarray:
         """Embeddings for a list of clips, concatenated in input order.  Clips of equal length are
         batched into one device call (the reference loops clip by clip, fad.py:317); clips at another sample
@@ -262,6 +278,8 @@ class FrechetAudioDistance:
                 if self.verbose:
                     print(f"[Exported FAD] Error processing audio: {e}")
                 prepared.append(None)
+        if not on_device:
+            prepared = [a if a is None else self._canonical_length(a) for a in prepared]
         by_len: Dict[int, List[int]] = {}
         for i, a in enumerate(prepared):
             if a is not None:

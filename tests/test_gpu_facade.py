@@ -158,6 +158,26 @@ def test_clap_facade():
     assert np.max(np.abs(el - pipeline.OracleFAD("clap", sd).embed_clip(long))) / np.max(np.abs(ref)) < 1e-4
 
 
+def test_ragged_clips_share_device_batches(fad_vgg):
+    # clips whose lengths differ only past the last complete 0.96 s patch are one device batch (cut to the samples the
+    # patches read); the embeddings are those of the clips embedded one by one
+    rng = np.random.default_rng(3)
+    lens = [16000 + 400 + int(k) for k in rng.integers(0, 15000, size=6)] + [2 * 16000 + 7, 3 * 16000 - 11]
+    clips = [synth.background_clip(i, n) for i, n in enumerate(lens)]
+    calls = []
+    orig = fad_vgg._embed_group
+    fad_vgg._embed_group = lambda c, rows, rs: (calls.append((len(c), c[0].shape[0])), orig(c, rows, rs))[1]
+    try:
+        out = fad_vgg.get_embeddings(clips, 16000)
+    finally:
+        fad_vgg._embed_group = orig
+    assert len(calls) <= 3 and sum(c[0] for c in calls) == len(clips)          # 1-, 2- and 3-patch groups at most
+    one = np.concatenate([fad_vgg.get_embeddings([c], 16000) for c in clips], axis=0)
+    assert out.shape == one.shape and np.array_equal(out, one)
+    ref = pipeline.OracleFAD("vggish", networks.vggish_random_state_dict(seed=0)).get_embeddings(clips)
+    assert ref.shape == out.shape and np.max(np.abs(out - ref)) / np.max(np.abs(ref)) < 2.5e-3
+
+
 def test_clap_foreign_sample_rate_follows_reference_order():
     # get_embeddings(x, sr != 48000): the reference pads to 480000 samples at the SOURCE rate (fad.py:355-359),
     # int16-truncates (clap.py:70-72), then resamples (clap.py:75-80) and keeps 1001 frames (fad.py:87-89)

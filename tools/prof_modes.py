@@ -16,6 +16,7 @@ g = torch.Generator(device="cuda").manual_seed(1)
 pcm = (torch.randn(n, 10 * sr, device="cuda", generator=g) * 0.1).clamp(-1, 1)
 for rep in range(2):
     for name, prec, env in (("bf16", "bf16", {}), ("fp16", "fp16", {}), ("fp16x2 (e4m3 lo pass)", "fp16x2", {"FADB_LO_FP8": "1"}),
+                            ("fp16x2 (e4m3, not Cin=64)", "fp16x2", {"FADB_LO_FP8": "1", "FADB_LO_FP8_C64": "0"}),
                             ("fp16x2 (fp16 lo pass)", "fp16x2", {"FADB_LO_FP8": "0"})):
         os.environ.update(env)
         eng = Engine(model, sd, precision=prec)
