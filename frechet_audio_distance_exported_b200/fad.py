@@ -334,7 +334,7 @@ class FrechetAudioDistance:
         round trip per clip, fad.py:389-396)."""
         eng = self.engine
         n, length, dtype = len(clips), clips[0].shape[0], torch.from_numpy(clips[0][:1]).dtype
-        chunk = max(1, min(n, self._chunk_clips(length)))
+        chunk = max(1, min(n, self._chunk_clips(length, staged=True)))
         depth = 3
         # pinned staging: flat byte buffers that only grow, viewed as [chunk, length] of this group's dtype — pinning
         # costs about a millisecond per megabyte, and a ragged directory is many groups (one per length)
@@ -385,11 +385,12 @@ class FrechetAudioDistance:
             self._stage_used[slot] = True
             slot = (slot + 1) % depth
 
-    def _chunk_clips(self, n_samples: int) -> int:
-        """clips per host->device chunk: about 160 MB of fp32 PCM (256 .. 1024 ten-second 16 kHz clips measured within
-        2 % of each other on a B200; the smaller chunk halves the one-off cost of pinning the three staging buffers,
-        ~1 ms per MB)"""
-        return max(1, min(256, (160 << 20) // max(4 * n_samples, 1)))
+    def _chunk_clips(self, n_samples: int, staged: bool = False) -> int:
+        """clips per host->device chunk: about 320 MB of fp32 PCM (512 ten-second 16 kHz clips were measured best on a
+        B200, 256 .. 1024 within 2 %).  `staged` (get_embeddings: the chunk passes through pinned staging buffers that
+        this object allocates) halves it — pinning costs ~1 ms per MB, once."""
+        cap, nbytes = (256, 160 << 20) if staged else (512, 320 << 20)
+        return max(1, min(cap, nbytes // max(4 * n_samples, 1)))
 
     def _ring(self) -> HostRing:
         if getattr(self, "_host_ring", None) is None:
