@@ -493,13 +493,18 @@ def run_b200(args):
     # (640 000 B of PCM read + 245 760 B of fp32 patches); the fused kernel also runs conv1, so it writes the
     # pooled conv1 activations (1 966 080 B per clip, 16-bit) instead of the patches
     clips_step = 2 * (hi - lo)
+    # bytes the fused kernel really moves per clip: PCM in, 16-bit conv1 activations out, and in fp16x2 their W-padded
+    # e4m3 copy (48 x 34 x 64 per patch) for conv2's low-order pass
+    actual_clip = 640000 + 10 * 48 * 32 * 64 * 2 + (10 * 48 * 34 * 64 if args.precision == "fp16x2" and
+                                                      os.environ.get("FADB_LO_FP8_C64", "1") != "0" and
+                                                      os.environ.get("FADB_LO_FP8", "1") != "0" else 0)
     frontend = {"bound": "hbm", "achieved": clips_step * 885760 / (front_ms * 1e-3) / 1e9 if front_ms > 0 else None,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": clips_step * 885760 / (front_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if front_ms > 0 else None,
                 "kernel": "fadb_vggish_front_conv1_tc_kernel (fp64 FFT log-mel front end fused with tcgen05 conv1)",
                 "ms_per_step": front_ms, "step_share": front_ms / ms_step if ms_step > 0 else None,
-                "actual_bytes_per_clip": 640000 + 10 * 48 * 32 * 64 * 2,
-                "actual_gbs": clips_step * (640000 + 10 * 48 * 32 * 64 * 2) / (front_ms * 1e-3) / 1e9 if front_ms > 0 else None}
+                "actual_bytes_per_clip": actual_clip,
+                "actual_gbs": clips_step * actual_clip / (front_ms * 1e-3) / 1e9 if front_ms > 0 else None}
 
     # ---- the other precision modes, device-resident, 2 timed steps each (same data, same step function)
     modes = {args.precision: {"value": value, "ms_per_step": ms_step, "fad": fad_value, "mma_passes": passes}}
