@@ -178,3 +178,14 @@ def test_host_ring_chunking():
     assert chunk_bounds(0, 4) == [] and chunk_bounds(3, 8) == [(0, 3)]
     b = chunk_bounds(12500, 512, first=256)
     assert sum(n for _, n in b) == 12500 and all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+
+
+def test_threaded_gather_into_staging_rows():
+    # fad.py::_gather_clips: the four-thread copy of a clip list into the rows of a staging buffer is the plain loop
+    from frechet_audio_distance_exported_b200.fad import _gather_clips
+    rng = np.random.default_rng(0)
+    for n, length, dt in [(3, 1000, np.float32), (64, 4096, np.float32), (37, 777, np.int16)]:
+        clips = [(rng.standard_normal(length) * 1000).astype(dt) for _ in range(n + 5)]
+        view = np.zeros((n, length), dtype=dt)
+        _gather_clips(view, clips, 2, n)
+        assert np.array_equal(view, np.stack(clips[2:2 + n]))
